@@ -1,0 +1,147 @@
+/*
+ * tinycarlo_b200.h — C ABI of libtinycarlo_b200.so: the B200-native batched replacement of tinycarlo's
+ * per-step hot path.  Plain pointers and sizes only; no torch, no C++ types.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference checkout):
+ *   tc_create              TinyCarloEnv.__init__ staging: Map.__init__ (tinycarlo/map.py:9-37), Layer tables
+ *                          (tinycarlo/layer.py:15-19), Car.__init__ (tinycarlo/car.py:10-32)
+ *   tc_set_car_params      Car.__init__ parameters (tinycarlo/car.py:12-18), one row per env
+ *   tc_set_camera_params   Camera.__init__/update_params (tinycarlo/camera.py:12-27,48-50): E (3x4), K, max_range,
+ *                          line_thickness per env; E and K are built on the host (camera.py:145-178)
+ *   tc_reset               TinyCarloEnv.reset -> Car.reset -> Map.sample_spawn (env.py:101-113, car.py:34-44,
+ *                          map.py:51-69) for the masked envs, spawn nodes drawn by the caller
+ *   tc_step                TinyCarloEnv.step (env.py:115-147): Car.step + find_local_path (car.py:70-148),
+ *                          Camera.capture_frame (camera.py:52-110), Renderer.render_camera_frame_classes/_rgb
+ *                          (renderer.py:36-51), Car.get_info (car.py:46-68), default reward/termination (env.py:87-99)
+ *   tc_render              Camera.capture_frame alone at the current poses (used after tc_reset / tc_set_state)
+ *   tc_get_state/set_state direct access to Car.position/rotation/steering_angle/velocity/local_path/last_maneuver
+ *   tc_step_host           the same step driven with HOST buffers (pinned or pageable): actions are copied in and the
+ *                          scalar results copied out inside the call; used for the end-to-end measurement
+ *
+ * Conventions: every function returns 0 on success or a negative TcError; tc_last_error() gives the message of the
+ * last failure on the calling thread. Pointers named dev_* are CUDA device pointers on the handle's device, host_*
+ * are host pointers. All work is enqueued on the given stream (a cudaStream_t passed as void*, NULL = legacy
+ * default stream) and nothing synchronises unless documented. A handle is not thread-safe; distinct handles are.
+ * There is no CPU implementation behind this ABI: without a CUDA device every call fails with TC_ERR_CUDA.
+ */
+#ifndef TINYCARLO_B200_H
+#define TINYCARLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TC_ABI_VERSION 1
+#if defined(__GNUC__)
+#define TC_API __attribute__((visibility("default")))
+#else
+#define TC_API
+#endif
+
+typedef struct TcHandle TcHandle;
+
+typedef enum {
+    TC_OK = 0,
+    TC_ERR_INVALID = -1, /* bad argument */
+    TC_ERR_CUDA = -2,    /* CUDA runtime error (message has the cudaError string) */
+    TC_ERR_ALLOC = -3,
+    TC_ERR_STATE = -4 /* call order (e.g. step before params were set) */
+} TcError;
+
+/* Row layouts of the per-env arrays (all row-major, one row per env). */
+enum { TC_SF_X = 0, TC_SF_Y, TC_SF_ROT, TC_SF_STEER_DEG, TC_SF_VEL, TC_SF_FRONT_X, TC_SF_FRONT_Y, TC_SF_PAD, TC_SF_N = 8 };
+enum { TC_SI_PATH_LEN = 0, TC_SI_LAST_MANEUVER = 1, TC_SI_PATH_NODES = 2 /* 4 x (n0,n1) */, TC_SI_PATH_EDGES = 10 /* 4 */, TC_SI_N = 16 };
+enum { TC_CP_WHEELBASE = 0, TC_CP_TRACK_WIDTH, TC_CP_MAX_VELOCITY, TC_CP_MAX_STEERING_DEG, TC_CP_STEERING_SPEED /* NaN = None */,
+       TC_CP_MAX_ACCELERATION /* NaN = None */, TC_CP_MAX_DECELERATION, TC_CP_DT, TC_CP_N = 8 };
+enum { TC_CAM_E = 0 /* 12: row-major 3x4 */, TC_CAM_FX = 12, TC_CAM_FY, TC_CAM_CX, TC_CAM_CY, TC_CAM_MAX_RANGE, TC_CAM_N = 20 };
+enum { TC_OBS_CLASSES = 0 /* u8 [N,C,H,W], 0/255 */, TC_OBS_RGB = 1 /* u8 [N,H,W,3], layer colours */ };
+/* info_f64 row: cte, heading_error, velocity, reward, then C laneline distances */
+enum { TC_INFO_CTE = 0, TC_INFO_HEADING, TC_INFO_VELOCITY, TC_INFO_REWARD, TC_INFO_DIST0 = 4 };
+
+/* Map tables (HOST pointers; copied to the device by tc_create). Class order = key order of "lanelines" in the map JSON. */
+typedef struct {
+    int32_t n_classes;
+    const int32_t *ll_node_off; /* [C+1] first node of each class in ll_nodes */
+    const int32_t *ll_edge_off; /* [C+1] first edge of each class in ll_edges */
+    const double *ll_nodes;     /* [sumN][2] metres */
+    const int32_t *ll_edges;    /* [sumE][2] class-local node ids, JSON order */
+    const uint8_t *ll_colors;   /* [C][3] layer_color as stored in the JSON */
+    int32_t lp_n_nodes, lp_n_edges;
+    const double *lp_nodes;      /* [P][2] metres */
+    const int32_t *lp_edges;     /* [Q][2] */
+    const double *lp_orient;     /* [Q] atan2(n1-n0) of every lanepath edge, computed by the host libm */
+    const double *lp_orient_rev; /* [Q] atan2(n0-n1) */
+} TcMapDesc;
+
+typedef struct {
+    int32_t height, width; /* camera resolution, uniform over the handle's envs */
+    int32_t obs_format;    /* TC_OBS_CLASSES or TC_OBS_RGB */
+} TcSimDesc;
+
+/* Device output pointers of a step; any pointer may be NULL to skip that output. */
+typedef struct {
+    uint8_t *obs;              /* see TC_OBS_*; NULL = no rendering (reference: no_observation) */
+    float *cte;                /* [N] */
+    float *heading_error;      /* [N] */
+    float *velocity;           /* [N] */
+    float *reward;             /* [N] default reward (0 when wrapped) */
+    float *position;           /* [N,2] rear axle */
+    float *orientation;        /* [N] */
+    float *laneline_distances; /* [N,C] */
+    int32_t *nearest_edge;     /* [N,C] class-local index of the nearest laneline edge (-1: empty info) */
+    float *local_path;         /* [N,4,2] coordinates of the end node of each local-path edge (0 beyond path_len) */
+    int32_t *local_path_nodes; /* [N,4,2] node pairs (-1 beyond path_len) */
+    int32_t *path_len;         /* [N] */
+    uint8_t *terminated;       /* [N] default termination (0 when wrapped) */
+    uint8_t *truncated;        /* [N] */
+    double *info_f64;          /* [N,4+C] float64 mirror of the scalar info (parity tests) */
+    int32_t *seg_count;        /* [N,C] debug: projected segments per class */
+    int32_t *seg_i32;          /* [N,sumE,4] debug: (x0,y0,x1,y1) after the int32 cast; class c starts at slot ll_edge_off[c] */
+} TcOutputs;
+
+TC_API int tc_abi_version(void);
+TC_API const char *tc_last_error(void);
+
+TC_API int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int32_t device, TcHandle **out);
+TC_API int tc_destroy(TcHandle *h);
+
+TC_API int tc_set_car_params(TcHandle *h, const double *dev_params /*[N,TC_CP_N]*/, void *stream);
+TC_API int tc_set_camera_params(TcHandle *h, const double *dev_cam /*[N,TC_CAM_N]*/, const int32_t *dev_thickness /*[N]*/, void *stream);
+TC_API int tc_set_wrapped(TcHandle *h, int32_t wrapped); /* 1: reward 0 / terminated false (env.py:137-138) */
+
+/* Reset the envs with dev_mask[i] != 0 (NULL = all) to lanepath node dev_spawn_nodes[i]; renders into obs if non-NULL
+ * and zeroes their info outputs like the reference's reset (car.py:47-51). */
+TC_API int tc_reset(TcHandle *h, const uint8_t *dev_mask, const int32_t *dev_spawn_nodes, const TcOutputs *outs, void *stream);
+TC_API int tc_step(TcHandle *h, const float *dev_car_control /*[N,2]*/, const int32_t *dev_maneuver /*[N]*/, const TcOutputs *outs, void *stream);
+TC_API int tc_render(TcHandle *h, const uint8_t *dev_mask, uint8_t *dev_obs, int32_t obs_format, int32_t *dev_seg_count, int32_t *dev_seg_i32, void *stream);
+
+TC_API int tc_get_state(TcHandle *h, double *dev_sf /*[N,TC_SF_N]*/, int32_t *dev_si /*[N,TC_SI_N]*/, void *stream);
+TC_API int tc_set_state(TcHandle *h, const double *dev_sf, const int32_t *dev_si, void *stream);
+
+/* Host-buffer step: copies the actions in, runs tc_step, copies reward/terminated/truncated/cte/heading_error back and
+ * synchronises the stream. Any host output may be NULL. */
+TC_API int tc_step_host(TcHandle *h, const float *host_car_control, const int32_t *host_maneuver, const TcOutputs *dev_outs,
+                 float *host_reward, uint8_t *host_terminated, uint8_t *host_truncated, float *host_cte, float *host_heading_error,
+                 void *stream);
+
+/* Number of kernel launches issued through this handle since creation (bench.py reports it). */
+TC_API int64_t tc_launch_count(const TcHandle *h);
+
+/* Per-kernel device timing of tc_step with CUDA events recorded on the step's own stream (bench.py's roofline figure).
+ * tc_profile_begin arms up to max_steps steps; tc_profile_end waits for them and returns the summed milliseconds of the
+ * tracking, camera-pass and rasterise+store kernels and the number of steps recorded. */
+TC_API int tc_profile_begin(TcHandle *h, int32_t max_steps);
+TC_API int tc_profile_end(TcHandle *h, double *host_ms_sum /*[3]*/, int32_t *host_steps);
+
+/* Test hook: the reference's Layer queries (layer.py) evaluated by the DEVICE functions on class 0 of the handle's map.
+ * op: 0 get_nearest_edge(pos) 1 get_nearest_edge_with_orientation(pos, a) 2 is_position_within_edge_bounds(pos, e=(i0,i1))
+ *     3 distance_to_edge(pos, e) 4 clip_angle(a).  Results: out_i[0], out_d[0] (device pointers). */
+TC_API int tc_debug_layer_query(TcHandle *h, int32_t op, double px, double py, double a, int32_t i0, int32_t i1, int32_t *dev_out_i,
+                         double *dev_out_d, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

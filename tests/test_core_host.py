@@ -1,0 +1,119 @@
+"""CPU checks of the arithmetic the CUDA kernels run (tinycarlo_b200/csrc/tc_core.cuh built for the host, one lane per
+group; tests/hosttest_util.py): the node-parallel clip passes, the closed-form rasteriser and the CSR-based tracking are
+replayed against the reference's golden traces and fuzzed against cv2 / the oracle. The product never uses this build."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from golden_util import SCENARIOS, Golden
+from hosttest_util import HostCore, polyline
+from tinycarlo_b200.camera_params import camera_row
+from tinycarlo_b200.config import car_param_row, resolve_map_path
+from tinycarlo_b200.maptables import MapTables
+
+cv2 = pytest.importorskip("cv2")
+
+
+def cam_row_from(E, K, mr):
+    r = np.zeros(20)
+    r[:12] = np.asarray(E).reshape(-1)
+    r[12], r[13], r[14], r[15], r[16] = K[0][0], K[1][1], K[0][2], K[1][2], mr
+    return r
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_host_core_replays_reference_trace(name):
+    g = Golden(name)
+    cfg = g.cfg
+    tables = MapTables(resolve_map_path(cfg["map"], None), cfg["map"]["pixel_per_meter"], cfg["map"].get("spawn_points"))
+    cc = cfg["camera"]
+    row0 = camera_row(cc["position"], cc["orientation"], cc["fov"], cc["resolution"], cc["max_range"])
+    assert np.array_equal(row0[:12].reshape(3, 4), g["E"][0]) and row0[12] == g["K"][0][0][0] and row0[13] == g["K"][0][1][1]
+    env = HostCore(tables, 1, car_param_row(cfg["car"], 1 / cfg["sim"].get("fps", 30)), row0, cc["line_thickness"], g.H, g.W, g.fmt,
+                   wrapped=g.wrapped, rows_per_band=32 if g.H > 64 else 0)
+    mr = g.max_range_per_frame()
+    for f in range(g.F):
+        env.cam[0] = cam_row_from(g["E"][f], g["K"][f], mr[f])
+        if g["ev_kind"][f] == 0:
+            env.reset([int(g["spawn_node"][f])])
+        else:
+            t = int(g["ev_step"][f])
+            env.step(g["act_cc"][t][None], g["act_man"][t][None])
+            assert bool(env.truncated[0]) == bool(g["truncated"][f]), (name, f)
+            if not g.wrapped:
+                assert bool(env.terminated[0]) == bool(g["terminated"][f]), (name, f)
+                np.testing.assert_allclose(env.info[0, 3], g["reward"][f], rtol=1e-12, atol=1e-15)
+            np.testing.assert_allclose(env.info[0, 0], g["cte"][f], rtol=1e-12, atol=1e-15)
+            np.testing.assert_allclose(env.info[0, 1], g["heading"][f], rtol=1e-12, atol=1e-15)
+            assert env.info[0, 2] == g["velocity"][f]
+            np.testing.assert_allclose(env.info[0, 4:], g["dist"][f], rtol=1e-12, atol=1e-15)
+        sf, si = env.sf[0], env.si[0]
+        np.testing.assert_allclose(sf[:7], [*g["pos"][f], g["rot"][f], g["steer"][f], g["vel"][f], *g["front"][f]], rtol=1e-13, atol=1e-15)
+        L = int(g["lp_len"][f])
+        assert si[0] == L and si[1] == g["last_man"][f], (name, f)
+        assert np.array_equal(si[2:2 + 2 * L].reshape(L, 2), g["lp"][f][:L]), (name, f)
+        gi, _ = g.segments(f)
+        for c in range(g.C):
+            o = int(tables.ll_edge_off[c])
+            k = int(env.seg_count[0, c])
+            assert k == len(gi[c]), (name, f, c)
+            assert np.array_equal(env.seg[0, o:o + k], gi[c]), (name, f, c)
+        if g.fmt == "classes":
+            assert np.array_equal(env.obs[0], g.classes_frame(f)), (name, f)
+        else:
+            assert hashlib.sha256(env.obs[0].tobytes()).hexdigest().encode() == g["rgb_sha"][f], (name, f)
+
+
+@pytest.mark.parametrize("H,W,spread,n,nlanes", [(24, 32, 12, 4000, 1), (24, 32, 12, 3000, 32), (48, 64, 300, 2500, 32),
+                                                  (84, 84, 40, 1500, 32), (480, 640, 200, 120, 32)])
+def test_bitplane_rasteriser_vs_cv2(H, W, spread, n, nlanes):
+    rng = np.random.default_rng(H * 7 + W + nlanes)
+    bad = []
+    for _ in range(n):
+        t = int(rng.integers(1, 9))
+        p0 = (int(rng.integers(-spread, W + spread)), int(rng.integers(-spread, H + spread)))
+        p1 = (int(rng.integers(-spread, W + spread)), int(rng.integers(-spread, H + spread)))
+        a = np.zeros((H, W), np.uint8)
+        cv2.polylines(a, np.int32([[p0, p1]]), False, 255, t)
+        if not np.array_equal(a, polyline(H, W, p0, p1, t, nlanes=nlanes)):
+            bad.append((p0, p1, t))
+    assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("mag", [10**6, 10**9, 2**31 - 1])
+def test_bitplane_rasteriser_far_endpoints(mag):
+    rng = np.random.default_rng(mag % 9973)
+    H, W = 48, 64
+    bad = []
+    for _ in range(1500):
+        t = int(rng.integers(1, 7))
+        p0 = (int(rng.integers(-5, W + 5)), int(rng.integers(-5, H + 5)))
+        p1 = (int(rng.integers(-mag, mag + 1)), int(rng.integers(-mag, mag + 1)))
+        if rng.random() < 0.5:
+            p0, p1 = p1, p0
+        a = np.zeros((H, W), np.uint8)
+        cv2.polylines(a, np.int32([[p0, p1]]), False, 255, t)
+        if not np.array_equal(a, polyline(H, W, p0, p1, t, nlanes=32)):
+            bad.append((p0, p1, t))
+    assert not bad, bad[:5]
+    for t in (1, 2, 3):
+        for p0, p1 in [((10, 10), (-2**31, -2**31)), ((-2**31, 5), (20, 20)), ((30, -2**31), (30, 40)), ((-2**31, 20), (2**31 - 1, 20))]:
+            a = np.zeros((H, W), np.uint8)
+            cv2.polylines(a, np.int32([[p0, p1]]), False, 255, t)
+            assert np.array_equal(a, polyline(H, W, p0, p1, t, nlanes=32)), (p0, p1, t)
+
+
+def test_bitplane_bands_compose_to_full_frame():
+    """A band block only owns rows [y_lo, y_hi): the union of the bands must be the full-frame raster."""
+    rng = np.random.default_rng(5)
+    H, W = 96, 80
+    for _ in range(300):
+        t = int(rng.integers(1, 7))
+        p0 = (int(rng.integers(-30, W + 30)), int(rng.integers(-30, H + 30)))
+        p1 = (int(rng.integers(-30, W + 30)), int(rng.integers(-30, H + 30)))
+        full = polyline(H, W, p0, p1, t, nlanes=32)
+        parts = np.zeros_like(full)
+        for y in range(0, H, 32):
+            parts |= polyline(H, W, p0, p1, t, y_lo=y, y_hi=min(H, y + 32), nlanes=32)
+        assert np.array_equal(full, parts), (p0, p1, t)

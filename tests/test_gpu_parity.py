@@ -1,0 +1,232 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+ (1) the golden traces recorded from the unmodified reference (tests/golden/), and
+ (2) the CPU oracle on seeded batches of envs.
+Bars (BASELINE.json north_star): class masks, lanepath / segment indices bit-exact; pose, CTE, heading error, distances
+within 1e-5 relative in the exported fp32 tensors (the f64 mirrors are checked much tighter, see RTOL64)."""
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import SCENARIOS, Golden
+from pair_util import make_config, oracle_env, stanley_actions
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-5   # the north-star tolerance, on the fp32 outputs
+RTOL64 = 1e-9   # what the float64 state actually achieves (device libm differs from glibc by ulps only)
+
+
+def _vec(cfg, n, **kw):
+    from tinycarlo_b200 import TinyCarloVecEnv
+    return TinyCarloVecEnv(cfg, n, device="cuda:0", **kw)
+
+
+def cam_row_from(E, K, mr):
+    r = np.zeros(20)
+    r[:12] = np.asarray(E).reshape(-1)
+    r[12], r[13], r[14], r[15], r[16] = K[0][0], K[1][1], K[0][2], K[1][2], mr
+    return r
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_cuda_replays_reference_trace(name):
+    """One env driven with the recorded actions must reproduce the reference's trace."""
+    g = Golden(name)
+    env = _vec(g.cfg, 1, debug_segments=True)
+    if g.wrapped:
+        env.set_wrapped(True)
+    mr = g.max_range_per_frame()
+    off = env.map.ll_edge_off
+    last_cam = None
+    for f in range(g.F):
+        cam = cam_row_from(g["E"][f], g["K"][f], mr[f])
+        if last_cam is None or not np.array_equal(cam, last_cam):
+            env.set_camera_rows(cam[None])
+            last_cam = cam
+        if g["ev_kind"][f] == 0:
+            obs, info = env.reset(spawn_nodes=torch.tensor([int(g["spawn_node"][f])], dtype=torch.int32))
+        else:
+            t = int(g["ev_step"][f])
+            act = {"car_control": torch.tensor(g["act_cc"][t][None], dtype=torch.float32, device="cuda:0"),
+                   "maneuver": torch.tensor(g["act_man"][t][None], dtype=torch.int32, device="cuda:0")}
+            obs, reward, term, trunc, info = env.step(act)
+            i64 = env.out["info_f64"][0].cpu().numpy()
+            assert bool(trunc[0]) == bool(g["truncated"][f]), (name, f)
+            if not g.wrapped:
+                assert bool(term[0]) == bool(g["terminated"][f]), (name, f)
+                np.testing.assert_allclose(i64[3], g["reward"][f], rtol=RTOL64, atol=1e-12)
+                np.testing.assert_allclose(float(reward[0]), g["reward"][f], rtol=RTOL32, atol=1e-7)
+            np.testing.assert_allclose(i64[0], g["cte"][f], rtol=RTOL64, atol=1e-12)
+            np.testing.assert_allclose(i64[1], g["heading"][f], rtol=RTOL64, atol=1e-12)
+            np.testing.assert_allclose(i64[2], g["velocity"][f], rtol=RTOL64, atol=1e-12)
+            np.testing.assert_allclose(i64[4:], g["dist"][f], rtol=RTOL64, atol=1e-12)
+            np.testing.assert_allclose(float(info["cte"][0]), g["cte"][f], rtol=RTOL32, atol=1e-7)
+            np.testing.assert_allclose(float(info["heading_error"][0]), g["heading"][f], rtol=RTOL32, atol=1e-7)
+            np.testing.assert_allclose(info["laneline_distances"][0].cpu().numpy(), g["dist"][f], rtol=RTOL32, atol=1e-7)
+        st = env.state_dict()
+        sf, si = st["sf"][0].cpu().numpy(), st["si"][0].cpu().numpy()
+        np.testing.assert_allclose(sf[:7], [*g["pos"][f], g["rot"][f], g["steer"][f], g["vel"][f], *g["front"][f]], rtol=RTOL64, atol=1e-12)
+        L = int(g["lp_len"][f])
+        assert si[0] == L and si[1] == g["last_man"][f], (name, f)
+        assert np.array_equal(si[2:2 + 2 * L].reshape(L, 2), g["lp"][f][:L]), (name, f)
+        gi, _ = g.segments(f)
+        cnt = env.out["seg_count"][0].cpu().numpy()
+        seg = env.out["seg_i32"][0].cpu().numpy()
+        for c in range(g.C):
+            assert cnt[c] == len(gi[c]), (name, f, c)
+            assert np.array_equal(seg[off[c]:off[c] + cnt[c]], gi[c]), (name, f, c)
+        o = obs[0].cpu().numpy()
+        if g.fmt == "classes":
+            assert np.array_equal(o, g.classes_frame(f)), (name, f)
+            if f % 10 == 0:
+                rgb = env.render_rgb()[0].cpu().numpy()
+                assert hashlib.sha256(rgb.tobytes()).hexdigest().encode() == g["rgb_sha"][f], (name, f)
+        else:
+            assert hashlib.sha256(o.tobytes()).hexdigest().encode() == g["rgb_sha"][f], (name, f)
+    env.close()
+
+
+def _compare_batch(env, oenv, step, stats):
+    st = env.state_dict()
+    sf, si = st["sf"].cpu().numpy(), st["si"].cpu().numpy()
+    np.testing.assert_allclose(sf[:, :7], oenv.sf[:, :7], rtol=RTOL64, atol=1e-11, err_msg=f"state step {step}")
+    assert np.array_equal(si[:, :10], oenv.si[:, :10]), f"local path step {step}"
+    i64 = env.out["info_f64"].cpu().numpy()
+    np.testing.assert_allclose(i64, oenv.info, rtol=RTOL64, atol=1e-11, err_msg=f"info step {step}")
+    assert np.array_equal(env.out["nearest_edge"].cpu().numpy(), oenv.nearest), f"nearest laneline edge step {step}"
+    assert np.array_equal(env.out["terminated"].cpu().numpy(), oenv.terminated), f"terminated step {step}"
+    assert np.array_equal(env.out["truncated"].cpu().numpy(), oenv.truncated), f"truncated step {step}"
+    # fp32 exports at the north-star tolerance
+    np.testing.assert_allclose(env.out["cte"].cpu().numpy(), oenv.cte, rtol=RTOL32, atol=1e-7)
+    np.testing.assert_allclose(env.out["heading_error"].cpu().numpy(), oenv.heading_error, rtol=RTOL32, atol=1e-7)
+    np.testing.assert_allclose(env.out["laneline_distances"].cpu().numpy(), oenv.dist, rtol=RTOL32, atol=1e-7)
+    np.testing.assert_allclose(env.out["position"].cpu().numpy(), oenv.sf[:, :2], rtol=RTOL32, atol=1e-7)
+    obs = env.obs.cpu().numpy()
+    bad = int((obs != oenv.obs).reshape(obs.shape[0], -1).any(axis=1).sum())
+    stats["frames"] += obs.shape[0]
+    stats["bad_frames"] += bad
+    assert bad == 0, f"{bad} of {obs.shape[0]} frames differ from the oracle at step {step}"
+
+
+@pytest.mark.parametrize("map_name,fmt,res,n,steps,policy", [
+    ("knuffingen", "classes", [128, 160], 1024, 40, "stanley"),
+    ("knuffingen", "classes", [480, 640], 64, 25, "stanley_mixed"),
+    ("simple_layout", "classes", [84, 84], 2048, 30, "random"),
+    ("simple_layout", "rgb", [96, 128], 512, 25, "random"),
+    ("formula_student_track", "classes", [64, 96], 512, 30, "random_forward"),
+])
+def test_cuda_batch_matches_oracle(map_name, fmt, res, n, steps, policy):
+    """Lockstep batches with auto-reset: every step, every env, against the oracle."""
+    cfg = make_config(map_name, fmt, cam={"resolution": res, "max_range": 0.5 if "formula" not in map_name else 1.5},
+                      car={"max_velocity": 0.15} if map_name == "simple_layout" else None,
+                      spawn="default" if "formula" not in map_name else None)
+    env = _vec(cfg, n)
+    oenv = oracle_env(cfg, n)
+    rng = np.random.default_rng(zlib.crc32(f"{map_name}{fmt}{n}".encode()))
+    env.reset(seed=123)
+    spawn = env._spawn_nodes.cpu().numpy()
+    oenv.reset(spawn)
+    stats = {"frames": 0, "bad_frames": 0}
+    assert np.array_equal(env.obs.cpu().numpy(), oenv.obs)
+    man = rng.integers(0, 4, n).astype(np.int32) if policy != "stanley" else np.zeros(n, np.int32)
+    for t in range(steps):
+        if policy.startswith("stanley"):
+            cc = stanley_actions(oenv.cte.copy(), oenv.heading_error.copy(), cfg["car"]["max_steering_angle"])
+            cc[:, 1] += rng.normal(0, 0.2, n).astype(np.float32)
+            if policy == "stanley_mixed" and t % 8 == 0:
+                man = rng.integers(0, 4, n).astype(np.int32)
+        elif policy == "random":
+            cc = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+            man = rng.integers(0, 4, n).astype(np.int32)
+        else:
+            cc = np.stack([rng.uniform(0.2, 1, n), rng.uniform(-1, 1, n)], 1).astype(np.float32)
+            man = rng.integers(0, 4, n).astype(np.int32)
+        env.step({"car_control": torch.from_numpy(cc).cuda(), "maneuver": torch.from_numpy(man).cuda()})
+        oenv.step(cc.astype(np.float64), man)
+        _compare_batch(env, oenv, t, stats)
+        done = (oenv.terminated | oenv.truncated).astype(bool)
+        if done.any():
+            env.reset_done()
+            sp = env._spawn_nodes.cpu().numpy()
+            oenv.reset(sp, mask=done)
+            assert np.array_equal(env.obs.cpu().numpy(), oenv.obs), f"frames after reset, step {t}"
+            st = env.state_dict()
+            np.testing.assert_allclose(st["sf"].cpu().numpy()[:, :7], oenv.sf[:, :7], rtol=RTOL64, atol=1e-11)
+    assert stats["bad_frames"] == 0
+    env.close()
+
+
+def test_cuda_per_env_params_match_oracle():
+    """Config-5 style domain randomisation: per-env camera pose / fov / range / thickness and car parameters."""
+    n = 512
+    cfg = make_config("knuffingen", "classes", cam={"resolution": [120, 160]})
+    rng = np.random.default_rng(77)
+    env = _vec(cfg, n)
+    pos = np.stack([rng.uniform(-0.01, 0.02, n), rng.uniform(-0.01, 0.01, n), rng.uniform(0.02, 0.08, n)], 1).round(4)
+    ori = np.stack([rng.integers(5, 40, n), rng.integers(-5, 6, n), rng.integers(-30, 31, n)], 1).astype(np.float64)
+    fov = rng.integers(60, 130, n).astype(np.float64)
+    mr = rng.uniform(0.3, 2.0, n).round(3)
+    th = rng.integers(1, 7, n).astype(np.int32)
+    env.set_camera_params(position=pos, orientation=ori, fov=fov, max_range=mr, line_thickness=th)
+    wb = rng.uniform(0.04, 0.06, n)
+    mv = rng.uniform(0.08, 0.3, n)
+    ms = rng.uniform(24, 36, n)
+    env.set_car_params(wheelbase=wb, max_velocity=mv, max_steering_angle=ms)
+    oenv = oracle_env(cfg, n, cam_rows=env._cam_rows.copy(), thickness=th, car_rows=env._car_rows.copy())
+    env.reset(seed=5)
+    oenv.reset(env._spawn_nodes.cpu().numpy())
+    assert np.array_equal(env.obs.cpu().numpy(), oenv.obs)
+    stats = {"frames": 0, "bad_frames": 0}
+    for t in range(25):
+        cc = stanley_actions(oenv.cte.copy(), oenv.heading_error.copy(), ms)
+        cc[:, 1] += rng.normal(0, 0.3, n).astype(np.float32)
+        man = rng.integers(0, 4, n).astype(np.int32) if t % 6 == 0 else np.zeros(n, np.int32)
+        env.step({"car_control": torch.from_numpy(cc).cuda(), "maneuver": torch.from_numpy(man).cuda()})
+        oenv.step(cc.astype(np.float64), man)
+        _compare_batch(env, oenv, t, stats)
+    env.close()
+
+
+def test_cuda_layer_known_answers():
+    """The reference's own unit-test answers (test/test_layer.py, test/test_helper.py) on the DEVICE functions."""
+    import layer_kats as K
+    from tinycarlo_b200 import TinyCarloVecEnv
+
+    def env_for(nodes, edges):
+        data = {"width": 100, "height": 100,
+                "lanelines": {"test": {"layer_color": [0, 0, 0], "nodes": [list(map(float, p)) for p in nodes], "edges": [list(e) for e in edges]}},
+                "lanepath": {"layer_color": [0, 0, 0], "nodes": [[0.0, 0.0], [1.0, 0.0]], "edges": [[0, 1]]}}
+        import json, tempfile, os
+        d = tempfile.mkdtemp()
+        with open(os.path.join(d, "m.json"), "w") as fh:
+            json.dump(data, fh)
+        cfg = {"sim": {"observation_space_format": "classes"}, "car": {}, "camera": {"resolution": [8, 8], "max_range": 1.0},
+               "map": {"json_path": os.path.join(d, "m.json"), "pixel_per_meter": 1}}
+        return TinyCarloVecEnv(cfg, 1, device="cuda:0")
+
+    for nodes, edges, cases in K.NEAREST_EDGE:
+        env = env_for(nodes, edges)
+        for pos, want in cases:
+            assert env.debug_layer_query(0, pos)[0] == want, (pos, want)
+    for nodes, edges, cases in K.NEAREST_EDGE_ORIENT:
+        env = env_for(nodes, edges)
+        for (pos, o), want in cases:
+            assert env.debug_layer_query(1, pos, angle=o)[0] == (-1 if want is None else want), (pos, o, want)
+    for nodes, edges, cases in K.WITHIN_BOUNDS:
+        env = env_for(nodes, edges)
+        for pos, want in cases:
+            assert bool(env.debug_layer_query(2, pos, edge=edges[0])[0]) == want, (nodes, edges, pos)
+    for nodes, edges, cases in K.DISTANCE_TO_EDGE_EXACT:
+        env = env_for(nodes, edges)
+        for pos, want in cases:
+            assert env.debug_layer_query(3, pos, edge=edges[0])[1] == want
+    for nodes, edges, cases in K.DISTANCE_TO_EDGE_CLOSE:
+        env = env_for(nodes, edges)
+        for pos, want in cases:
+            assert abs(env.debug_layer_query(3, pos, edge=edges[0])[1] - want) < 1e-5
+    env = env_for([(0, 0), (1, 0)], [(0, 1)])
+    for a, want in K.CLIP_ANGLE:
+        assert env.debug_layer_query(4, angle=a)[1] == want

@@ -1,0 +1,403 @@
+// tc_api.cu — the C ABI of libtinycarlo_b200.so (see include/tinycarlo_b200.h for what each call replaces).
+// Host side: table packing/staging, per-env device buffers, launch configuration. No torch, no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tc_kernels.cuh"
+#include "tc_pack.h"
+
+static thread_local std::string g_last_error;
+static int tc_fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+#define TC_CUDA(expr)                                                                                                        \
+    do {                                                                                                                     \
+        cudaError_t _e = (expr);                                                                                             \
+        if (_e != cudaSuccess) return tc_fail(TC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+    } while (0)
+
+struct TcHandle {
+    int device = 0;
+    int n_envs = 0, C = 0, H = 0, W = 0, obs_format = 0;
+    int sum_nodes = 0, sum_edges = 0, max_nodes = 0;
+    int wrapped = 0;
+    bool car_set = false, cam_set = false;
+    int64_t launches = 0;
+    TcBlobLayout layout{};
+    std::vector<void *> allocs;
+    unsigned char *d_blob = nullptr;
+    TcClassTables *d_classes = nullptr;
+    int32_t *d_edge_off = nullptr;
+    double *d_sf = nullptr;
+    int32_t *d_si = nullptr;
+    double *d_car = nullptr, *d_cam = nullptr, *d_pose = nullptr;
+    int32_t *d_thick = nullptr;
+    int32_t *d_seg = nullptr, *d_seg_count = nullptr;
+    float *d_act_cc = nullptr; // staging for tc_step_host
+    int32_t *d_act_man = nullptr;
+    float *d_h_reward = nullptr, *d_h_cte = nullptr, *d_h_heading = nullptr;
+    uint8_t *d_h_term = nullptr, *d_h_trunc = nullptr;
+    uint8_t colors[TC_MAX_CLASSES * 3] = {0};
+    // raster launch geometry
+    int rows_per_band_cls = 0, n_bands_cls = 0, plane_words_cls = 0;
+    int rows_per_band_rgb = 0, n_bands_rgb = 0, plane_words_rgb = 0;
+    size_t track_smem = 0, proj_smem = 0;
+    // optional per-kernel CUDA-event timing (tc_profile_begin/end)
+    bool profiling = false;
+    int prof_cap = 0, prof_used = 0; // step slots
+    std::vector<cudaEvent_t> prof_ev; // 4 events per slot: before track, after track, after project, after raster
+};
+
+template <typename T>
+static int tc_dev_alloc(TcHandle *h, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return tc_fail(TC_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = (T *)q;
+    return TC_OK;
+}
+#define TC_TRY(expr)             \
+    do {                         \
+        int _r = (expr);         \
+        if (_r != TC_OK) return _r; \
+    } while (0)
+
+// rows per band so that rows*W*bytes_per_px is a multiple of 16 (vector stores stay aligned band to band when the
+// frame base is) and the bit planes fit the shared-memory budget
+static void tc_band_geometry(int H, int W, int planes, size_t smem_budget, int *rows_per_band, int *n_bands, int *plane_words) {
+    int rows = H;
+    auto words = [&](int r) { return (int)(((size_t)r * W + 31) / 32) + 1; };
+    while (rows > 1 && (size_t)words(rows) * 4 * planes > smem_budget) rows = (rows + 1) / 2;
+    if (rows < H) {
+        int q = 16; // rows multiple of 16 keeps every band start 16-byte aligned for any W
+        rows = ((rows + q - 1) / q) * q;
+        while (rows > q && (size_t)words(rows) * 4 * planes > smem_budget) rows -= q;
+        if (rows > H) rows = H;
+    }
+    *rows_per_band = rows;
+    *n_bands = (H + rows - 1) / rows;
+    *plane_words = words(rows);
+}
+
+extern "C" {
+
+int tc_abi_version(void) { return TC_ABI_VERSION; }
+const char *tc_last_error(void) { return g_last_error.c_str(); }
+
+int tc_destroy(TcHandle *h) {
+    if (!h) return TC_OK;
+    cudaSetDevice(h->device);
+    for (void *p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    delete h;
+    return TC_OK;
+}
+
+int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int32_t device, TcHandle **out) {
+    if (!map || !sim || !out) return tc_fail(TC_ERR_INVALID, "tc_create: null argument");
+    if (num_envs <= 0) return tc_fail(TC_ERR_INVALID, "tc_create: num_envs must be positive");
+    const int C = map->n_classes;
+    if (C <= 0 || C > TC_MAX_CLASSES) return tc_fail(TC_ERR_INVALID, "tc_create: n_classes out of range (1..16)");
+    if (sim->height <= 0 || sim->width <= 0) return tc_fail(TC_ERR_INVALID, "tc_create: bad resolution");
+    if (sim->obs_format != TC_OBS_CLASSES && sim->obs_format != TC_OBS_RGB) return tc_fail(TC_ERR_INVALID, "tc_create: bad obs_format");
+    TcPacked pk;
+    {
+        std::string err = tc_pack_map(map, pk);
+        if (!err.empty()) return tc_fail(TC_ERR_INVALID, "tc_create: " + err);
+    }
+    const int sumN = map->ll_node_off[C], sumE = map->ll_edge_off[C];
+    int ndev = 0;
+    TC_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return tc_fail(TC_ERR_INVALID, "tc_create: no such CUDA device");
+    TC_CUDA(cudaSetDevice(device));
+
+    TcHandle *h = new TcHandle();
+    h->device = device; h->n_envs = num_envs; h->C = C; h->H = sim->height; h->W = sim->width; h->obs_format = sim->obs_format;
+    h->sum_nodes = sumN; h->sum_edges = sumE;
+    memcpy(h->colors, map->ll_colors, (size_t)3 * C);
+    h->max_nodes = pk.max_nodes;
+    h->layout = pk.L;
+    const TcBlobLayout &L = h->layout;
+    h->track_smem = (size_t)L.total_bytes;
+    if (h->track_smem > 200 * 1024) { tc_destroy(h); return tc_fail(TC_ERR_INVALID, "tc_create: map tables exceed the shared-memory staging budget (200 KB)"); }
+
+#define TC_TRYH(expr)                  \
+    do {                               \
+        int _r = (expr);               \
+        if (_r != TC_OK) {             \
+            tc_destroy(h);             \
+            return _r;                 \
+        }                              \
+    } while (0)
+#define TC_CUDAH(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess) {                                                                            \
+            tc_destroy(h);                                                                                  \
+            return tc_fail(TC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+        }                                                                                                   \
+    } while (0)
+
+    TC_TRYH(tc_dev_alloc(h, &h->d_blob, pk.blob.size()));
+    TC_CUDAH(cudaMemcpy(h->d_blob, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice));
+    // per-class tables for the camera pass: views into the device blob + node adjacency CSR
+    int32_t *d_adj = nullptr;
+    TC_TRYH(tc_dev_alloc(h, &d_adj, pk.adj.size()));
+    TC_CUDAH(cudaMemcpy(d_adj, pk.adj.data(), pk.adj.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<TcClassTables> cls;
+    tc_class_views(map, pk, h->d_blob, d_adj, cls);
+    TC_TRYH(tc_dev_alloc(h, &h->d_classes, (size_t)C));
+    TC_CUDAH(cudaMemcpy(h->d_classes, cls.data(), sizeof(TcClassTables) * C, cudaMemcpyHostToDevice));
+    TC_TRYH(tc_dev_alloc(h, &h->d_edge_off, (size_t)C + 1));
+    TC_CUDAH(cudaMemcpy(h->d_edge_off, map->ll_edge_off, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice));
+
+    // ---- per-env buffers
+    const size_t N = (size_t)num_envs;
+    TC_TRYH(tc_dev_alloc(h, &h->d_sf, N * TC_SF_N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_si, N * TC_SI_N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_car, N * TC_CP_N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_cam, N * TC_CAM_N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_pose, N * 12));
+    TC_TRYH(tc_dev_alloc(h, &h->d_thick, N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_seg, N * (size_t)std::max(sumE, 1) * 4));
+    TC_TRYH(tc_dev_alloc(h, &h->d_seg_count, N * C));
+    TC_TRYH(tc_dev_alloc(h, &h->d_act_cc, N * 2));
+    TC_TRYH(tc_dev_alloc(h, &h->d_act_man, N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_h_reward, N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_h_cte, N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_h_heading, N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_h_term, N));
+    TC_TRYH(tc_dev_alloc(h, &h->d_h_trunc, N));
+    TC_CUDAH(cudaMemset(h->d_sf, 0, N * TC_SF_N * sizeof(double)));
+    TC_CUDAH(cudaMemset(h->d_si, 0xff, N * TC_SI_N * sizeof(int32_t)));
+    TC_CUDAH(cudaMemset(h->d_seg_count, 0, N * C * sizeof(int32_t)));
+    TC_CUDAH(cudaMemset(h->d_pose, 0, N * 12 * sizeof(double)));
+
+    // ---- kernel attributes / launch geometry
+    h->proj_smem = tc_proj_smem_bytes(h->max_nodes);
+    const size_t plane_budget = 48 * 1024;
+    tc_band_geometry(h->H, h->W, 1, plane_budget, &h->rows_per_band_cls, &h->n_bands_cls, &h->plane_words_cls);
+    tc_band_geometry(h->H, h->W, C + 1, 2 * plane_budget, &h->rows_per_band_rgb, &h->n_bands_rgb, &h->plane_words_rgb);
+    TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->track_smem));
+    TC_CUDAH(cudaFuncSetAttribute(tc_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->proj_smem));
+    TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->plane_words_cls * 4)));
+    TC_CUDAH(cudaFuncSetAttribute(tc_raster_rgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((size_t)h->plane_words_rgb * 4 * (C + 1))));
+    *out = h;
+    return TC_OK;
+}
+
+int tc_set_car_params(TcHandle *h, const double *dev_params, void *stream) {
+    if (!h || !dev_params) return tc_fail(TC_ERR_INVALID, "tc_set_car_params: null argument");
+    TC_CUDA(cudaSetDevice(h->device));
+    TC_CUDA(cudaMemcpyAsync(h->d_car, dev_params, (size_t)h->n_envs * TC_CP_N * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    h->car_set = true;
+    return TC_OK;
+}
+
+int tc_set_camera_params(TcHandle *h, const double *dev_cam, const int32_t *dev_thickness, void *stream) {
+    if (!h || !dev_cam || !dev_thickness) return tc_fail(TC_ERR_INVALID, "tc_set_camera_params: null argument");
+    TC_CUDA(cudaSetDevice(h->device));
+    TC_CUDA(cudaMemcpyAsync(h->d_cam, dev_cam, (size_t)h->n_envs * TC_CAM_N * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    TC_CUDA(cudaMemcpyAsync(h->d_thick, dev_thickness, (size_t)h->n_envs * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    h->cam_set = true;
+    return TC_OK;
+}
+
+int tc_set_wrapped(TcHandle *h, int32_t wrapped) {
+    if (!h) return tc_fail(TC_ERR_INVALID, "tc_set_wrapped: null handle");
+    h->wrapped = wrapped ? 1 : 0;
+    return TC_OK;
+}
+
+static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int obs_format, int32_t *seg_count_out, int32_t *seg_out,
+                            cudaStream_t st, cudaEvent_t after_project = nullptr) {
+    const int N = h->n_envs, C = h->C;
+    TcProjArgs pa;
+    pa.classes = h->d_classes; pa.n_envs = N; pa.n_classes = C; pa.sum_edges = h->sum_edges; pa.max_nodes = h->max_nodes;
+    pa.H = h->H; pa.W = h->W; pa.edge_off = h->d_edge_off; pa.pose = h->d_pose; pa.cam = h->d_cam; pa.mask = mask;
+    pa.seg = seg_out ? seg_out : h->d_seg;
+    pa.seg_count = seg_count_out ? seg_count_out : h->d_seg_count;
+    tc_project_kernel<<<N * C, TC_PROJ_THREADS, h->proj_smem, st>>>(pa);
+    h->launches++;
+    TC_CUDA(cudaGetLastError());
+    if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
+    if (!obs) return TC_OK;
+    TcRasterArgs ra;
+    ra.n_envs = N; ra.n_classes = C; ra.sum_edges = h->sum_edges; ra.H = h->H; ra.W = h->W;
+    ra.edge_off = h->d_edge_off; ra.thickness = h->d_thick; ra.mask = mask; ra.seg = pa.seg; ra.seg_count = pa.seg_count; ra.obs = obs;
+    memcpy(ra.colors, h->colors, sizeof(ra.colors));
+    if (obs_format == TC_OBS_CLASSES) {
+        ra.rows_per_band = h->rows_per_band_cls; ra.n_bands = h->n_bands_cls; ra.plane_words = h->plane_words_cls;
+        tc_raster_classes_kernel<<<N * C * ra.n_bands, TC_RASTER_THREADS, (size_t)ra.plane_words * 4, st>>>(ra);
+    } else {
+        ra.rows_per_band = h->rows_per_band_rgb; ra.n_bands = h->n_bands_rgb; ra.plane_words = h->plane_words_rgb;
+        tc_raster_rgb_kernel<<<N * ra.n_bands, TC_RASTER_THREADS, (size_t)ra.plane_words * 4 * (C + 1), st>>>(ra);
+    }
+    h->launches++;
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
+static int tc_launch_track(TcHandle *h, int mode, const float *cc, const int32_t *man, const uint8_t *mask, const int32_t *spawn,
+                           const TcOutputs *outs, cudaStream_t st) {
+    TcTrackArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.blob = h->d_blob; ta.layout = h->layout; ta.n_envs = h->n_envs; ta.mode = mode; ta.wrapped = h->wrapped;
+    ta.sf = h->d_sf; ta.si = h->d_si; ta.car = h->d_car; ta.cam = h->d_cam; ta.pose = h->d_pose;
+    ta.act_cc = cc; ta.act_man = man; ta.mask = mask; ta.spawn_nodes = spawn;
+    if (outs) ta.out = *outs;
+    const int envs_per_block = TC_TRACK_THREADS / 32;
+    tc_track_kernel<<<(h->n_envs + envs_per_block - 1) / envs_per_block, TC_TRACK_THREADS, h->track_smem, st>>>(ta);
+    h->launches++;
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
+int tc_reset(TcHandle *h, const uint8_t *dev_mask, const int32_t *dev_spawn_nodes, const TcOutputs *outs, void *stream) {
+    if (!h || !dev_spawn_nodes) return tc_fail(TC_ERR_INVALID, "tc_reset: null argument");
+    if (!h->car_set || !h->cam_set) return tc_fail(TC_ERR_STATE, "tc_reset: car/camera parameters not set");
+    TC_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TC_TRY(tc_launch_track(h, 1, nullptr, nullptr, dev_mask, dev_spawn_nodes, outs, st));
+    if (outs && (outs->obs || outs->seg_count || outs->seg_i32))
+        TC_TRY(tc_launch_render(h, dev_mask, outs->obs, h->obs_format, outs->seg_count, outs->seg_i32, st));
+    return TC_OK;
+}
+
+int tc_step(TcHandle *h, const float *dev_car_control, const int32_t *dev_maneuver, const TcOutputs *outs, void *stream) {
+    if (!h || !dev_car_control || !dev_maneuver) return tc_fail(TC_ERR_INVALID, "tc_step: null argument");
+    if (!h->car_set || !h->cam_set) return tc_fail(TC_ERR_STATE, "tc_step: car/camera parameters not set");
+    TC_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool prof = h->profiling && h->prof_used < h->prof_cap;
+    cudaEvent_t *ev = prof ? &h->prof_ev[(size_t)4 * h->prof_used] : nullptr;
+    if (prof) TC_CUDA(cudaEventRecord(ev[0], st));
+    TC_TRY(tc_launch_track(h, 0, dev_car_control, dev_maneuver, nullptr, nullptr, outs, st));
+    if (prof) TC_CUDA(cudaEventRecord(ev[1], st));
+    if (outs && (outs->obs || outs->seg_count || outs->seg_i32))
+        TC_TRY(tc_launch_render(h, nullptr, outs->obs, h->obs_format, outs->seg_count, outs->seg_i32, st, prof ? ev[2] : nullptr));
+    else if (prof) TC_CUDA(cudaEventRecord(ev[2], st));
+    if (prof) {
+        TC_CUDA(cudaEventRecord(ev[3], st));
+        h->prof_used++;
+    }
+    return TC_OK;
+}
+
+// recompute the camera poses from the current state (after tc_set_state / camera parameter changes)
+__global__ void tc_pose_kernel(int n, const double *sf, const double *cam, double *pose) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *s = sf + (size_t)i * TC_SF_N;
+    tc_camera_pose(cam + (size_t)i * TC_CAM_N + TC_CAM_E, s[TC_SF_X], s[TC_SF_Y], cos(s[TC_SF_ROT]), sin(s[TC_SF_ROT]), pose + (size_t)i * 12);
+}
+
+int tc_render(TcHandle *h, const uint8_t *dev_mask, uint8_t *dev_obs, int32_t obs_format, int32_t *dev_seg_count, int32_t *dev_seg_i32,
+              void *stream) {
+    if (!h) return tc_fail(TC_ERR_INVALID, "tc_render: null handle");
+    if (!h->cam_set) return tc_fail(TC_ERR_STATE, "tc_render: camera parameters not set");
+    if (obs_format != TC_OBS_CLASSES && obs_format != TC_OBS_RGB) return tc_fail(TC_ERR_INVALID, "tc_render: bad obs_format");
+    TC_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    tc_pose_kernel<<<(h->n_envs + 127) / 128, 128, 0, st>>>(h->n_envs, h->d_sf, h->d_cam, h->d_pose);
+    h->launches++;
+    TC_CUDA(cudaGetLastError());
+    return tc_launch_render(h, dev_mask, dev_obs, obs_format, dev_seg_count, dev_seg_i32, st);
+}
+
+int tc_get_state(TcHandle *h, double *dev_sf, int32_t *dev_si, void *stream) {
+    if (!h) return tc_fail(TC_ERR_INVALID, "tc_get_state: null handle");
+    TC_CUDA(cudaSetDevice(h->device));
+    if (dev_sf) TC_CUDA(cudaMemcpyAsync(dev_sf, h->d_sf, (size_t)h->n_envs * TC_SF_N * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (dev_si) TC_CUDA(cudaMemcpyAsync(dev_si, h->d_si, (size_t)h->n_envs * TC_SI_N * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TC_OK;
+}
+
+int tc_set_state(TcHandle *h, const double *dev_sf, const int32_t *dev_si, void *stream) {
+    if (!h) return tc_fail(TC_ERR_INVALID, "tc_set_state: null handle");
+    TC_CUDA(cudaSetDevice(h->device));
+    if (dev_sf) TC_CUDA(cudaMemcpyAsync(h->d_sf, dev_sf, (size_t)h->n_envs * TC_SF_N * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (dev_si) TC_CUDA(cudaMemcpyAsync(h->d_si, dev_si, (size_t)h->n_envs * TC_SI_N * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TC_OK;
+}
+
+int tc_step_host(TcHandle *h, const float *host_car_control, const int32_t *host_maneuver, const TcOutputs *dev_outs, float *host_reward,
+                 uint8_t *host_terminated, uint8_t *host_truncated, float *host_cte, float *host_heading_error, void *stream) {
+    if (!h || !host_car_control || !host_maneuver) return tc_fail(TC_ERR_INVALID, "tc_step_host: null argument");
+    TC_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)h->n_envs;
+    TC_CUDA(cudaMemcpyAsync(h->d_act_cc, host_car_control, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    TC_CUDA(cudaMemcpyAsync(h->d_act_man, host_maneuver, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    TcOutputs o;
+    if (dev_outs) o = *dev_outs; else memset(&o, 0, sizeof(o));
+    if (!o.reward) o.reward = h->d_h_reward;
+    if (!o.terminated) o.terminated = h->d_h_term;
+    if (!o.truncated) o.truncated = h->d_h_trunc;
+    if (!o.cte) o.cte = h->d_h_cte;
+    if (!o.heading_error) o.heading_error = h->d_h_heading;
+    TC_TRY(tc_step(h, h->d_act_cc, h->d_act_man, &o, stream));
+    if (host_reward) TC_CUDA(cudaMemcpyAsync(host_reward, o.reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (host_terminated) TC_CUDA(cudaMemcpyAsync(host_terminated, o.terminated, N, cudaMemcpyDeviceToHost, st));
+    if (host_truncated) TC_CUDA(cudaMemcpyAsync(host_truncated, o.truncated, N, cudaMemcpyDeviceToHost, st));
+    if (host_cte) TC_CUDA(cudaMemcpyAsync(host_cte, o.cte, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (host_heading_error) TC_CUDA(cudaMemcpyAsync(host_heading_error, o.heading_error, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    TC_CUDA(cudaStreamSynchronize(st));
+    return TC_OK;
+}
+
+int64_t tc_launch_count(const TcHandle *h) { return h ? h->launches : 0; }
+
+int tc_profile_begin(TcHandle *h, int32_t max_steps) {
+    if (!h || max_steps <= 0) return tc_fail(TC_ERR_INVALID, "tc_profile_begin: bad argument");
+    TC_CUDA(cudaSetDevice(h->device));
+    while ((int)h->prof_ev.size() < 4 * max_steps) {
+        cudaEvent_t e;
+        TC_CUDA(cudaEventCreate(&e));
+        h->prof_ev.push_back(e);
+    }
+    h->prof_cap = max_steps;
+    h->prof_used = 0;
+    h->profiling = true;
+    return TC_OK;
+}
+
+int tc_profile_end(TcHandle *h, double *host_ms_sum /*[3]: track, project, raster*/, int32_t *host_steps) {
+    if (!h || !host_ms_sum || !host_steps) return tc_fail(TC_ERR_INVALID, "tc_profile_end: null argument");
+    TC_CUDA(cudaSetDevice(h->device));
+    host_ms_sum[0] = host_ms_sum[1] = host_ms_sum[2] = 0;
+    for (int i = 0; i < h->prof_used; i++) {
+        cudaEvent_t *ev = &h->prof_ev[(size_t)4 * i];
+        TC_CUDA(cudaEventSynchronize(ev[3]));
+        for (int k = 0; k < 3; k++) {
+            float ms = 0;
+            TC_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            host_ms_sum[k] += ms;
+        }
+    }
+    *host_steps = h->prof_used;
+    h->profiling = false;
+    h->prof_used = 0;
+    return TC_OK;
+}
+
+int tc_debug_layer_query(TcHandle *h, int32_t op, double px, double py, double a, int32_t i0, int32_t i1, int32_t *dev_out_i,
+                         double *dev_out_d, void *stream) {
+    if (!h || !dev_out_i || !dev_out_d) return tc_fail(TC_ERR_INVALID, "tc_debug_layer_query: null argument");
+    TC_CUDA(cudaSetDevice(h->device));
+    tc_debug_layer_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_blob, h->layout, op, px, py, a, i0, i1, dev_out_i, dev_out_d);
+    h->launches++;
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
+} // extern "C"

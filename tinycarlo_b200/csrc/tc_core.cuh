@@ -1,0 +1,693 @@
+// tc_core.cuh — the arithmetic of the hot path as lane-parallel __host__ __device__ code.
+//
+// Everything here is written once and compiled twice: by nvcc into the sm_100a kernels of libtinycarlo_b200.so
+// (tc_kernels.cu: a warp per env for tracking, a block per (env, class) for the camera pass, a block per plane for
+// rasterise+store), and by g++ into the CPU-only test library libtc_hosttest.so (tc_hosttest.cpp), where a "group"
+// is one lane, so the parallel formulations can be checked in a container without a GPU. The product never loads
+// the host build.
+//
+// Floating point: the reference computes in float64 with numpy/BLAS; parity needs the same operation order.
+// Built with -fmad=false (nvcc) / -ffp-contract=off (g++): a*b+c is never fused implicitly, and the places where the
+// reference's OpenBLAS dgemm fuses (k-ordered FMA chains, probed on numpy 2.3.5) use fma() explicitly.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/tinycarlo_b200.h"
+
+#if defined(__CUDACC__)
+#define TC_HD __host__ __device__ __forceinline__
+#else
+#define TC_HD inline
+#endif
+
+#define TC_PI 3.14159265358979323846
+#define TC_MAX_CLASSES 16
+
+// ------------------------------------------------------------------------------------------------ lane groups
+// A group of cooperating lanes: a warp on the device, a single lane on the host.
+struct TcLanes {
+    int lane, n;
+};
+
+// lexicographic (value, index) minimum over the group; every lane receives the result. Ties -> lowest index
+// (layer.py:44 `d.index(min(d))`).
+TC_HD void tc_group_argmin(const TcLanes &g, double &d, int &idx) {
+#if defined(__CUDA_ARCH__)
+    for (int off = 16; off > 0; off >>= 1) {
+        double od = __shfl_xor_sync(0xffffffffu, d, off);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (oi >= 0 && (idx < 0 || od < d || (od == d && oi < idx))) {
+            d = od;
+            idx = oi;
+        }
+    }
+#else
+    (void)g; (void)d; (void)idx;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ small math
+// helper.py:11-19
+TC_HD double tc_clip_angle(double a) {
+    while (a > TC_PI) a -= 2 * TC_PI;
+    while (a < -TC_PI) a += 2 * TC_PI;
+    return a;
+}
+// layer.py:187 (the reference squares with pow(x, 2.0); x*x is its correctly rounded value)
+TC_HD double tc_dist(double ax, double ay, double bx, double by) {
+    double dx = ax - bx, dy = ay - by;
+    return sqrt(dx * dx + dy * dy);
+}
+// np.clip on float64 scalars
+TC_HD double tc_np_clip(double x, double lo, double hi) {
+    double m = x > lo ? x : lo;
+    return m < hi ? m : hi;
+}
+// numpy float64 -> int32 cast (renderer.py:43,50): truncation, NaN/inf/out of range -> INT_MIN (x86 cvttsd2si)
+TC_HD int32_t tc_np_int32(double v) {
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return INT32_MIN;
+    return (int32_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------ map tables
+// Views into the packed table blob (global memory, or the shared-memory copy a block staged with TMA).
+struct TcTrackTables {
+    int n_classes;
+    int lp_n_nodes, lp_n_edges;
+    const double *lp_nodes;      // [P][2]
+    const double *lp_orient;     // [Q]
+    const double *lp_orient_rev; // [Q]
+    const double *ll_nodes;      // [sumN][2]
+    const int32_t *lp_edges;     // [Q][2]
+    const int32_t *next_off;     // [P+1] CSR over lanepath edges by start node (edge-list order, layer.py:183)
+    const int32_t *next_edge;    // [Q]
+    const int32_t *prev_off;     // [P+1] CSR by end node (layer.py:185)
+    const int32_t *prev_edge;    // [Q]
+    const int32_t *ll_edges;     // [sumE][2] class-local node ids
+    const int32_t *ll_node_off;  // [C+1]
+    const int32_t *ll_edge_off;  // [C+1]
+};
+
+// Byte offsets of the sections inside the blob (all multiples of 16); filled by the host at staging.
+struct TcBlobLayout {
+    int32_t n_classes, lp_n_nodes, lp_n_edges, sum_nodes, sum_edges;
+    int32_t off_lp_nodes, off_lp_orient, off_lp_orient_rev, off_ll_nodes, off_lp_edges, off_next_off, off_next_edge, off_prev_off,
+        off_prev_edge, off_ll_edges, off_ll_node_off, off_ll_edge_off;
+    int32_t total_bytes;
+};
+
+TC_HD TcTrackTables tc_track_tables(const unsigned char *base, const TcBlobLayout &L) {
+    TcTrackTables t;
+    t.n_classes = L.n_classes;
+    t.lp_n_nodes = L.lp_n_nodes;
+    t.lp_n_edges = L.lp_n_edges;
+    t.lp_nodes = (const double *)(base + L.off_lp_nodes);
+    t.lp_orient = (const double *)(base + L.off_lp_orient);
+    t.lp_orient_rev = (const double *)(base + L.off_lp_orient_rev);
+    t.ll_nodes = (const double *)(base + L.off_ll_nodes);
+    t.lp_edges = (const int32_t *)(base + L.off_lp_edges);
+    t.next_off = (const int32_t *)(base + L.off_next_off);
+    t.next_edge = (const int32_t *)(base + L.off_next_edge);
+    t.prev_off = (const int32_t *)(base + L.off_prev_off);
+    t.prev_edge = (const int32_t *)(base + L.off_prev_edge);
+    t.ll_edges = (const int32_t *)(base + L.off_ll_edges);
+    t.ll_node_off = (const int32_t *)(base + L.off_ll_node_off);
+    t.ll_edge_off = (const int32_t *)(base + L.off_ll_edge_off);
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------ layer.py queries
+// layer.py:105-124 over a CSR slice [b, e) of lanepath edges incident to `node` (forward: edges leaving it, else
+// edges entering it). Returns the CSR position of the picked edge, -1 for None. The reference drops self-loops from
+// the orientation list but indexes the unfiltered list with the winner; kept.
+TC_HD int tc_pick_edge(const TcTrackTables &t, int node, double orientation, const int32_t *csr, int b, int e, bool forward) {
+    int n = e - b;
+    if (n == 0) return -1;
+    if (n <= 1) return b;
+    int k = 0, best = -1;
+    double bd = 0;
+    for (int i = b; i < e; i++) {
+        int ed = csr[i];
+        int nn = forward ? t.lp_edges[2 * ed + 1] : t.lp_edges[2 * ed];
+        if (nn == node) continue;
+        double o = forward ? t.lp_orient[ed] : t.lp_orient_rev[ed];
+        double d = fabs(tc_clip_angle(o - orientation));
+        if (best < 0 || d < bd) {
+            best = k;
+            bd = d;
+        }
+        k++;
+    }
+    if (best < 0) return -1;
+    return b + best;
+}
+
+// layer.py:126-142 on explicit node coordinates
+TC_HD bool tc_within_edge_bounds(double px, double py, double n0x, double n0y, double n1x, double n1y) {
+    if (px == n0x && py == n0y) return true;
+    if (px == n1x && py == n1y) return true;
+    double ex = n1x - n0x, ey = n1y - n0y;
+    double a0 = fabs(tc_clip_angle(atan2(py - n0y, px - n0x) - atan2(ey, ex)));
+    double a1 = fabs(tc_clip_angle(atan2(py - n1y, px - n1x) - atan2(-ey, -ex)));
+    return a0 <= TC_PI / 2 && a1 <= TC_PI / 2;
+}
+// layer.py:144-164
+TC_HD double tc_distance_to_edge(double px, double py, double n1x, double n1y, double n2x, double n2y) {
+    double lx = n2x - n1x, ly = n2y - n1y;
+    double vx = px - n1x, vy = py - n1y;
+    if (lx == 0) return ly > 0 ? px - n1x : n1x - px;
+    return (vx * ly - vy * lx) / sqrt(lx * lx + ly * ly);
+}
+// layer.py:33-44 / 59-74: argmin over edges [0, m) of |d(p,n0)+d(p,n1)|, optionally restricted to lanepath edges whose
+// orientation is within `lim` rad of `orientation`. Group-parallel; every lane gets the winner (-1: none).
+TC_HD int tc_nearest_edge(const TcLanes &g, const double *nodes, const int32_t *edges, int m, double px, double py,
+                          const double *orient, double orientation, double lim) {
+    int best = -1;
+    double bd = 0;
+    for (int e = g.lane; e < m; e += g.n) {
+        if (orient && !(fabs(tc_clip_angle(orient[e] - orientation)) <= lim)) continue;
+        int a = edges[2 * e], b = edges[2 * e + 1];
+        double d = fabs(tc_dist(px, py, nodes[2 * a], nodes[2 * a + 1]) + tc_dist(px, py, nodes[2 * b], nodes[2 * b + 1]));
+        if (best < 0 || d < bd) {
+            best = e;
+            bd = d;
+        }
+    }
+    tc_group_argmin(g, bd, best);
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------ car.py
+struct TcCarState {
+    double x, y, rot, steer, vel, fx, fy;
+    int path_len, last_man;
+    int pn[8]; // local_path node pairs
+    int pe[4]; // local_path edge ids
+};
+
+TC_HD void tc_load_state(const double *sf, const int32_t *si, TcCarState &s) {
+    s.x = sf[TC_SF_X]; s.y = sf[TC_SF_Y]; s.rot = sf[TC_SF_ROT]; s.steer = sf[TC_SF_STEER_DEG]; s.vel = sf[TC_SF_VEL];
+    s.fx = sf[TC_SF_FRONT_X]; s.fy = sf[TC_SF_FRONT_Y];
+    s.path_len = si[TC_SI_PATH_LEN]; s.last_man = si[TC_SI_LAST_MANEUVER];
+    for (int i = 0; i < 8; i++) s.pn[i] = si[TC_SI_PATH_NODES + i];
+    for (int i = 0; i < 4; i++) s.pe[i] = si[TC_SI_PATH_EDGES + i];
+}
+TC_HD void tc_store_state(double *sf, int32_t *si, const TcCarState &s) {
+    sf[TC_SF_X] = s.x; sf[TC_SF_Y] = s.y; sf[TC_SF_ROT] = s.rot; sf[TC_SF_STEER_DEG] = s.steer; sf[TC_SF_VEL] = s.vel;
+    sf[TC_SF_FRONT_X] = s.fx; sf[TC_SF_FRONT_Y] = s.fy; sf[TC_SF_PAD] = 0.0;
+    si[TC_SI_PATH_LEN] = s.path_len; si[TC_SI_LAST_MANEUVER] = s.last_man;
+    for (int i = 0; i < 8; i++) si[TC_SI_PATH_NODES + i] = s.pn[i];
+    for (int i = 0; i < 4; i++) si[TC_SI_PATH_EDGES + i] = s.pe[i];
+    si[14] = 0; si[15] = 0;
+}
+
+// car.py:127-148. Group-uniform control flow; only the u-turn scan is spread over the lanes. Returns truncated.
+TC_HD bool tc_find_local_path(const TcLanes &g, const TcTrackTables &t, TcCarState &s, int maneuver) {
+    double dir = tc_clip_angle(t.lp_orient[s.pe[0]] + maneuver * TC_PI / 2);
+    int ne; // new first edge
+    if (maneuver == 2 && s.last_man != 2) {
+        ne = tc_nearest_edge(g, t.lp_nodes, t.lp_edges, t.lp_n_edges, s.fx, s.fy, t.lp_orient, dir, 30.0 * (TC_PI / 180.0));
+        dir = tc_clip_angle(dir + TC_PI);
+        // reference: local_path=[None] -> TypeError at car.py:144. Here: truncated, path untouched.
+        if (ne < 0) return true;
+    } else {
+        // layer.py:77-103
+        int e0 = s.pn[0], e1 = s.pn[1];
+        int pn = tc_pick_edge(t, e1, dir, t.next_edge, t.next_off[e1], t.next_off[e1 + 1], true);
+        int pp = tc_pick_edge(t, e0, dir, t.prev_edge, t.prev_off[e0], t.prev_off[e0 + 1], false);
+        if (pn < 0 || pp < 0) return true;
+        int en = t.next_edge[pn], ep = t.prev_edge[pp];
+        int next_node = t.lp_edges[2 * en + 1], prev_node = t.lp_edges[2 * ep];
+        double d0 = tc_dist(s.fx, s.fy, t.lp_nodes[2 * e0], t.lp_nodes[2 * e0 + 1]);
+        double d1 = tc_dist(s.fx, s.fy, t.lp_nodes[2 * e1], t.lp_nodes[2 * e1 + 1]);
+        double dn = tc_dist(s.fx, s.fy, t.lp_nodes[2 * next_node], t.lp_nodes[2 * next_node + 1]);
+        double dp = tc_dist(s.fx, s.fy, t.lp_nodes[2 * prev_node], t.lp_nodes[2 * prev_node + 1]);
+        if (dn < d0 && dn < d1) ne = en;
+        else if (dp < d0 && dp < d1) ne = ep;
+        else ne = s.pe[0];
+    }
+    s.last_man = maneuver;
+    s.pe[0] = ne;
+    s.pn[0] = t.lp_edges[2 * ne];
+    s.pn[1] = t.lp_edges[2 * ne + 1];
+    s.path_len = 1;
+    for (int k = 0; k < 3; k++) {
+        int from = s.vel > 0 ? s.pn[2 * (s.path_len - 1) + 1] : s.pn[2 * (s.path_len - 1)];
+        int p = tc_pick_edge(t, from, dir, t.next_edge, t.next_off[from], t.next_off[from + 1], true);
+        if (p < 0) return true;
+        int e = t.next_edge[p];
+        s.pe[s.path_len] = e;
+        s.pn[2 * s.path_len] = from;
+        s.pn[2 * s.path_len + 1] = t.lp_edges[2 * e + 1];
+        s.path_len++;
+    }
+    return false;
+}
+
+// car.py:70-125 (v_cmd, s_cmd already clipped to [-1,1], env.py:118). cp = car parameter row. Returns truncated.
+TC_HD bool tc_car_step(const TcLanes &g, const TcTrackTables &t, const double *cp, TcCarState &s, double v_cmd, double s_cmd,
+                       int maneuver) {
+    double dt = cp[TC_CP_DT];
+    double nv = v_cmd * cp[TC_CP_MAX_VELOCITY];
+    if (!isnan(cp[TC_CP_MAX_ACCELERATION]))
+        nv = tc_np_clip(nv, s.vel - cp[TC_CP_MAX_DECELERATION] * dt, s.vel + cp[TC_CP_MAX_ACCELERATION] * dt);
+    s.vel = nv;
+    double ns = s_cmd * cp[TC_CP_MAX_STEERING_DEG];
+    if (!isnan(cp[TC_CP_STEERING_SPEED])) ns = tc_np_clip(ns, s.steer - cp[TC_CP_STEERING_SPEED] * dt, s.steer + cp[TC_CP_STEERING_SPEED] * dt);
+    s.steer = ns;
+    double vxn = cos(s.rot), vyn = sin(s.rot);
+    if (fabs(s.steer) < 0.0001) {
+        s.x = s.x + s.vel * vxn * dt;
+        s.y = s.y + s.vel * vyn * dt;
+    } else {
+        double radius = cp[TC_CP_WHEELBASE] / tan(s.steer * (TC_PI / 180.0));
+        double ang_vel = s.vel / radius;
+        double dyaw = ang_vel * dt;
+        double tx = vyn * radius, ty = -vxn * radius;
+        double c = cos(dyaw), sn = sin(dyaw);
+        // R_M.dot([tx, ty]) is an OpenBLAS dgemv: out_i = fma(R_i0, tx, R_i1 * ty)
+        double r0 = fma(c, tx, (-sn) * ty);
+        double r1 = fma(sn, tx, c * ty);
+        s.x = s.x - tx + r0;
+        s.y = s.y - ty + r1;
+        s.rot += dyaw;
+        if (s.rot > TC_PI) s.rot -= 2 * TC_PI;
+        else if (s.rot < -TC_PI) s.rot += 2 * TC_PI;
+    }
+    s.fx = s.x + cp[TC_CP_WHEELBASE] * cos(s.rot);
+    s.fy = s.y + cp[TC_CP_WHEELBASE] * sin(s.rot);
+    return tc_find_local_path(g, t, s, maneuver);
+}
+
+// car.py:34-44 + map.py:66-68 with the spawn node drawn by the caller; spawn_rot/spawn_edge are host tables
+// (first outgoing edge and its atan2). Returns false when the node has no successor (state untouched).
+TC_HD bool tc_car_reset(const TcTrackTables &t, const double *cp, TcCarState &s, int node) {
+    if (node < 0 || node >= t.lp_n_nodes || t.next_off[node] == t.next_off[node + 1]) return false;
+    int e = t.next_edge[t.next_off[node]];
+    s.x = t.lp_nodes[2 * node];
+    s.y = t.lp_nodes[2 * node + 1];
+    s.rot = t.lp_orient[e];
+    s.steer = 0.0;
+    s.vel = 0.0;
+    s.fx = s.x + cp[TC_CP_WHEELBASE] * cos(s.rot);
+    s.fy = s.y + cp[TC_CP_WHEELBASE] * sin(s.rot);
+    s.path_len = 1;
+    s.last_man = 0;
+    for (int i = 0; i < 8; i++) s.pn[i] = -1;
+    for (int i = 0; i < 4; i++) s.pe[i] = -1;
+    s.pe[0] = e;
+    s.pn[0] = node;
+    s.pn[1] = t.lp_edges[2 * e + 1];
+    return true;
+}
+
+// car.py:46-68 + env.py:83-99. Every lane returns the same values. dist/nearest have n_classes entries.
+struct TcInfo {
+    double cte, heading, velocity, reward;
+    bool terminated;
+};
+TC_HD TcInfo tc_get_info(const TcLanes &g, const TcTrackTables &t, const double *cp, const TcCarState &s, bool wrapped, double *dist,
+                         int *nearest) {
+    TcInfo r;
+    r.cte = 0; r.heading = 0; r.velocity = 0.0;
+    for (int c = 0; c < t.n_classes; c++) { dist[c] = 0; nearest[c] = -1; }
+    if (s.path_len >= 2) {
+        int a = s.pn[2], b = s.pn[3];
+        r.cte = tc_distance_to_edge(s.fx, s.fy, t.lp_nodes[2 * a], t.lp_nodes[2 * a + 1], t.lp_nodes[2 * b], t.lp_nodes[2 * b + 1]);
+        r.heading = tc_clip_angle(t.lp_orient[s.pe[1]] - s.rot);
+        for (int c = 0; c < t.n_classes; c++) {
+            const double *nodes = t.ll_nodes + 2 * t.ll_node_off[c];
+            const int32_t *edges = t.ll_edges + 2 * t.ll_edge_off[c];
+            int m = t.ll_edge_off[c + 1] - t.ll_edge_off[c];
+            int e = tc_nearest_edge(g, nodes, edges, m, s.x, s.y, nullptr, 0.0, 0.0);
+            nearest[c] = e;
+            if (e < 0) continue; // class without edges: the reference would raise on min([])
+            int n0 = edges[2 * e], n1 = edges[2 * e + 1];
+            double n0x = nodes[2 * n0], n0y = nodes[2 * n0 + 1], n1x = nodes[2 * n1], n1y = nodes[2 * n1 + 1];
+            if (tc_within_edge_bounds(s.x, s.y, n0x, n0y, n1x, n1y)) dist[c] = fabs(tc_distance_to_edge(s.x, s.y, n0x, n0y, n1x, n1y));
+            else {
+                double da = tc_dist(s.x, s.y, n0x, n0y), db = tc_dist(s.fx, s.fy, n1x, n1y);
+                dist[c] = db < da ? db : da;
+            }
+        }
+        r.velocity = s.vel;
+    }
+    if (wrapped) { r.reward = 0; r.terminated = false; }
+    else {
+        double rw = (-1 / cp[TC_CP_TRACK_WIDTH]) * r.cte + 1;
+        r.reward = 0 > rw ? 0 : rw;
+        r.terminated = r.cte > (cp[TC_CP_TRACK_WIDTH] * 10);
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ camera.py
+// numpy matmul == OpenBLAS dgemm on these shapes: c_ij = fma(a_i3,b_3j, fma(a_i2,b_2j, fma(a_i1,b_1j, a_i0*b_0j)))
+TC_HD void tc_mm_chain(const double *A, int ar, int ac, const double *B, int bc, double *C) {
+    for (int i = 0; i < ar; i++)
+        for (int j = 0; j < bc; j++) {
+            double s = A[i * ac] * B[j];
+            for (int k = 1; k < ac; k++) s = fma(A[i * ac + k], B[k * bc + j], s);
+            C[i * bc + j] = s;
+        }
+}
+// camera.py:61 with car.py:159-165: pose = E @ (Rz(-rot) @ T(-pos)); cr/sr = cos(rot)/sin(rot) (cos(-r)=cos r, sin(-r)=-sin r)
+TC_HD void tc_camera_pose(const double *E, double x, double y, double cr, double sr, double *pose) {
+    double c = cr, s = -sr;
+    double R[16] = {c, -s, 0, 0, s, c, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double T[16] = {1, 0, 0, -x, 0, 1, 0, -y, 0, 0, 1, 0, 0, 0, 0, 1};
+    double M[16];
+    tc_mm_chain(R, 4, 4, T, 4, M);
+    tc_mm_chain(E, 3, 4, M, 4, pose);
+}
+// camera.py:59,124-131: one node (x, y, 0, 1) through the 3x4 pose (dgemm FMA chain over k)
+TC_HD void tc_transform_node(const double *pose, double x, double y, double &X, double &Y, double &Z) {
+    double r[3];
+    for (int i = 0; i < 3; i++) {
+        double s = pose[4 * i] * x;
+        s = fma(pose[4 * i + 1], y, s);
+        s = fma(pose[4 * i + 2], 0.0, s);
+        s = fma(pose[4 * i + 3], 1.0, s);
+        r[i] = s;
+    }
+    X = r[0]; Y = r[1]; Z = r[2];
+}
+// camera.py:112-122: move `mv` along the edge towards `keep` onto the plane z = tz (NaN row when parallel)
+TC_HD void tc_move_to_z(double kx, double ky, double kz, double &mx, double &my, double &mz, double tz) {
+    double dx = kx - mx, dy = ky - my, dz = kz - mz;
+    if (dz == 0) {
+        mx = my = mz = NAN;
+        return;
+    }
+    double tt = (tz - mz) / dz;
+    double nx = mx + tt * dx, ny = my + tt * dy, nz = mz + tt * dz;
+    mx = nx; my = ny; mz = nz;
+}
+// camera.py:89,133-142: K @ P (dgemm FMA chain, K = [[fx,0,cx],[0,fy,cy],[0,0,1]]) / row 2
+TC_HD void tc_project(const double *cam, double X, double Y, double Z, double &u, double &v) {
+    double h0 = fma(cam[TC_CAM_CX], Z, fma(0.0, Y, cam[TC_CAM_FX] * X));
+    double h1 = fma(cam[TC_CAM_CY], Z, fma(cam[TC_CAM_FY], Y, 0.0 * X));
+    double h2 = fma(1.0, Z, fma(0.0, Y, 0.0 * X));
+    u = h0 / h2;
+    v = h1 / h2;
+}
+
+// Per-class tables for the camera pass (global memory).
+struct TcClassTables {
+    int n_nodes, n_edges;
+    const double *nodes;    // [n][2]
+    const int32_t *edges;   // [m][2]
+    const int32_t *out_off; // [n+1] CSR: edges leaving a node, in edge order
+    const int32_t *out_edge;
+    const int32_t *in_off; // [n+1] CSR: edges entering a node, in edge order
+    const int32_t *in_edge;
+};
+
+// Scratch of one camera pass (shared memory on the device).
+struct TcProjScratch {
+    double *Px, *Py, *Pz; // [n]
+    int32_t *ix, *iy;     // [n] projected coordinates after the int32 cast
+    uint8_t *front, *inr, *vis; // [n]
+};
+
+// One of the four ordered clip passes of camera.py:70-86 in node-parallel form. In the reference each pass walks a
+// list of edges fixed before the pass and moves one endpoint per edge, in edge order. All moves of a pass write nodes
+// whose flag is clear and read nodes whose flag is set, so moves of different nodes commute; for one node the edges
+// apply in CSR (= edge-list) order. `outgoing`: the moved node is e[0] (passes 1 and 3), else e[1] (passes 2 and 4).
+// Caller synchronises the group before and after; flags are updated in tc_clip_pass_commit after the sync.
+TC_HD bool tc_clip_pass_node(const TcClassTables &ct, const TcProjScratch &sc, const uint8_t *flag, int v, bool outgoing, double tz) {
+    if (flag[v]) return false;
+    const int32_t *off = outgoing ? ct.out_off : ct.in_off;
+    const int32_t *lst = outgoing ? ct.out_edge : ct.in_edge;
+    bool moved = false;
+    double mx = sc.Px[v], my = sc.Py[v], mz = sc.Pz[v];
+    for (int i = off[v]; i < off[v + 1]; i++) {
+        int e = lst[i];
+        int w = outgoing ? ct.edges[2 * e + 1] : ct.edges[2 * e];
+        if (!flag[w]) continue;
+        tc_move_to_z(sc.Px[w], sc.Py[w], sc.Pz[w], mx, my, mz, tz);
+        moved = true;
+    }
+    if (moved) { sc.Px[v] = mx; sc.Py[v] = my; sc.Pz[v] = mz; }
+    return moved;
+}
+
+// ------------------------------------------------------------------------------------------------ cv2.polylines
+// Rasterisation into a flat 1-bit plane: bit index = y*W + x, 32-bit words. SURVEY.md Appendix A (OpenCV 4.13.0,
+// LINE_8, shift 0, thickness t, 2-point open polyline with both caps). The scalar set-up (pre-clip, quad, walker
+// events) is computed redundantly by every lane; pixels are spread over the lanes through closed forms of the
+// incremental loops (all integer, hence exact).
+#define TC_XY_SHIFT 16
+#define TC_XY_ONE (1 << TC_XY_SHIFT)
+
+struct TcPlane {
+    uint32_t *bits; // flat bit plane
+    int H, W;
+    int y_lo, y_hi; // rows [y_lo, y_hi) of the frame live in this plane; bit index = (y-y_lo)*W + x
+};
+
+TC_HD void tc_or_word(uint32_t *p, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, m);
+#else
+    *p |= m;
+#endif
+}
+TC_HD void tc_put(const TcPlane &pl, int64_t x, int64_t y) {
+    if (x < 0 || x >= pl.W || y < pl.y_lo || y >= pl.y_hi) return;
+    int64_t b = (y - pl.y_lo) * pl.W + x;
+    tc_or_word(pl.bits + (b >> 5), 1u << (b & 31));
+}
+// inclusive span, x already clipped to [0, W-1]
+TC_HD void tc_hline(const TcPlane &pl, int y, int x1, int x2) {
+    if (y < pl.y_lo || y >= pl.y_hi || x2 < x1) return;
+    int b1 = (y - pl.y_lo) * pl.W + x1, b2 = (y - pl.y_lo) * pl.W + x2;
+    int w1 = b1 >> 5, w2 = b2 >> 5;
+    uint32_t m1 = 0xffffffffu << (b1 & 31), m2 = 0xffffffffu >> (31 - (b2 & 31));
+    if (w1 == w2) tc_or_word(pl.bits + w1, m1 & m2);
+    else {
+        tc_or_word(pl.bits + w1, m1);
+        for (int w = w1 + 1; w < w2; w++) tc_or_word(pl.bits + w, 0xffffffffu);
+        tc_or_word(pl.bits + w2, m2);
+    }
+}
+
+TC_HD bool tc_clip_line(int64_t w, int64_t h, int64_t &x1, int64_t &y1, int64_t &x2, int64_t &y2) {
+    if (w <= 0 || h <= 0) return false;
+    int64_t right = w - 1, bottom = h - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        int64_t a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += (int64_t)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += (int64_t)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += (int64_t)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += (int64_t)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// thickness <= 1: LineIterator (8-connected, left to right). Step i of the Bresenham walk sits at major offset i and
+// minor offset c_i = floor((2*dy*i + dx - 1) / (2*dx)) — the closed form of `err` staying in [-2dy, 2dx-2dy).
+TC_HD void tc_line_bresenham(const TcLanes &g, const TcPlane &pl, int64_t x1, int64_t y1, int64_t x2, int64_t y2) {
+    if (x1 < 0 || x1 >= pl.W || x2 < 0 || x2 >= pl.W || y1 < 0 || y1 >= pl.H || y2 < 0 || y2 >= pl.H)
+        if (!tc_clip_line(pl.W, pl.H, x1, y1, x2, y2)) return;
+    int64_t dx = x2 - x1, dy = y2 - y1;
+    int sy = 1;
+    if (dx < 0) { dx = -dx; dy = -dy; x1 = x2; y1 = y2; }
+    if (dy < 0) { dy = -dy; sy = -1; }
+    bool vert = dy > dx;
+    if (vert) { int64_t t = dx; dx = dy; dy = t; }
+    if (dx == 0) {
+        if (g.lane == 0) tc_put(pl, x1, y1);
+        return;
+    }
+    for (int64_t i = g.lane; i <= dx; i += g.n) {
+        int64_t c = (2 * dy * i + dx - 1) / (2 * dx);
+        if (vert) tc_put(pl, x1 + c, y1 + sy * i);
+        else tc_put(pl, x1 + i, y1 + sy * c);
+    }
+}
+
+// 16.16 DDA of the quad outline
+TC_HD void tc_line2(const TcLanes &g, const TcPlane &pl, int64_t x1, int64_t y1, int64_t x2, int64_t y2) {
+    if (!tc_clip_line((int64_t)pl.W << TC_XY_SHIFT, (int64_t)pl.H << TC_XY_SHIFT, x1, y1, x2, y2)) return;
+    int64_t dx = x2 - x1, dy = y2 - y1, ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, xs, ys, n;
+    bool xmajor = ax > ay;
+    if (xmajor) {
+        if (dx < 0) { dy = -dy; int64_t t; t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+        xs = TC_XY_ONE;
+        ys = (dy * TC_XY_ONE) / (ax | 1);
+        n = (x2 - x1) >> TC_XY_SHIFT;
+    } else {
+        if (dy < 0) { dx = -dx; int64_t t; t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+        xs = (dx * TC_XY_ONE) / (ay | 1);
+        ys = TC_XY_ONE;
+        n = (y2 - y1) >> TC_XY_SHIFT;
+    }
+    x1 += TC_XY_ONE >> 1;
+    y1 += TC_XY_ONE >> 1;
+    if (g.lane == 0) tc_put(pl, (x2 + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT, (y2 + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT);
+    if (xmajor) {
+        int64_t x0 = x1 >> TC_XY_SHIFT;
+        for (int64_t i = g.lane; i <= n; i += g.n) tc_put(pl, x0 + i, (y1 + i * ys) >> TC_XY_SHIFT);
+    } else {
+        int64_t y0 = y1 >> TC_XY_SHIFT;
+        for (int64_t i = g.lane; i <= n; i += g.n) tc_put(pl, (x1 + i * xs) >> TC_XY_SHIFT, y0 + i);
+    }
+}
+
+// FillConvexPoly (4 vertices, shift 16). The scan-line loop only changes walker state on rows where a walker reaches
+// the end of its polygon edge; between such rows x advances linearly, so every lane replays the (<= 5) events and the
+// rows of each span are spread over the lanes.
+TC_HD void tc_fill_convex_poly4(const TcLanes &g, const TcPlane &pl, const int64_t (*v)[2]) {
+    const int npts = 4;
+    const int64_t delta = TC_XY_ONE >> 1;
+    int imin = 0, edges = npts;
+    int64_t xmin = v[0][0], xmax = v[0][0], ymin = v[0][1], ymax = v[0][1];
+    int64_t p0x = v[npts - 1][0], p0y = v[npts - 1][1];
+    for (int i = 0; i < npts; i++) {
+        if (v[i][1] < ymin) { ymin = v[i][1]; imin = i; }
+        if (v[i][1] > ymax) ymax = v[i][1];
+        if (v[i][0] > xmax) xmax = v[i][0];
+        if (v[i][0] < xmin) xmin = v[i][0];
+        tc_line2(g, pl, p0x, p0y, v[i][0], v[i][1]);
+        p0x = v[i][0]; p0y = v[i][1];
+    }
+    xmin = (xmin + delta) >> TC_XY_SHIFT; xmax = (xmax + delta) >> TC_XY_SHIFT;
+    ymin = (ymin + delta) >> TC_XY_SHIFT; ymax = (ymax + delta) >> TC_XY_SHIFT;
+    if ((int)xmax < 0 || (int)ymax < 0 || (int)xmin >= pl.W || (int)ymin >= pl.H) return;
+    if (ymax > pl.H - 1) ymax = pl.H - 1;
+    int y = (int)ymin;
+    int e_idx[2] = {imin, imin}, e_di[2] = {1, npts - 1}, e_ye[2] = {y, y};
+    int64_t e_x[2] = {-TC_XY_ONE, -TC_XY_ONE}, e_dx[2] = {0, 0};
+    while (true) {
+        for (int i = 0; i < 2; i++) {
+            if (y >= e_ye[i]) {
+                int idx0 = e_idx[i], di = e_di[i];
+                int idx = idx0 + di;
+                if (idx >= npts) idx -= npts;
+                for (; edges-- > 0;) {
+                    int ty = (int)((v[idx][1] + delta) >> TC_XY_SHIFT);
+                    if (ty > y) {
+                        int64_t xs = v[idx0][0], xe = v[idx][0];
+                        e_ye[i] = ty;
+                        e_dx[i] = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+                        e_x[i] = xs;
+                        e_idx[i] = idx;
+                        break;
+                    }
+                    idx0 = idx;
+                    idx += di;
+                    if (idx >= npts) idx -= npts;
+                }
+            }
+        }
+        if (edges < 0) break;
+        // rows y .. y_end-1 share the walker state: next event is the smaller ye (both are > y here), capped by ymax
+        int y_end = e_ye[0] < e_ye[1] ? e_ye[0] : e_ye[1];
+        if (y_end > (int)ymax + 1) y_end = (int)ymax + 1;
+        if (y_end <= y) y_end = y + 1; // a walker that found no edge keeps its stale ye; advance row by row like the reference
+        int r0 = y < 0 ? 0 : y;
+        if (r0 < pl.y_lo) r0 = pl.y_lo;
+        int r1 = y_end < pl.y_hi ? y_end : pl.y_hi;
+        for (int r = r0 + g.lane; r < r1; r += g.n) {
+            int64_t xa = e_x[0] + (int64_t)(r - y) * e_dx[0], xb = e_x[1] + (int64_t)(r - y) * e_dx[1];
+            int64_t xl = xa > xb ? xb : xa, xr = xa > xb ? xa : xb;
+            int xx1 = (int)((xl + delta) >> TC_XY_SHIFT), xx2 = (int)((xr + delta) >> TC_XY_SHIFT);
+            if (xx2 >= 0 && xx1 < pl.W) {
+                if (xx1 < 0) xx1 = 0;
+                if (xx2 >= pl.W) xx2 = pl.W - 1;
+                tc_hline(pl, r, xx1, xx2);
+            }
+        }
+        e_x[0] += (int64_t)(y_end - y) * e_dx[0];
+        e_x[1] += (int64_t)(y_end - y) * e_dx[1];
+        y = y_end;
+        if (y > (int)ymax) break;
+    }
+}
+
+// filled midpoint circle; the (radius+1)-step outer loop is replayed by every lane, the 4 spans of a step go to lanes 0..3
+TC_HD void tc_circle_filled(const TcLanes &g, const TcPlane &pl, int cx, int cy, int radius) {
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    int it = 0;
+    while (dx >= dy) {
+        int y11 = cy - dy, y12 = cy + dy, y21 = cy - dx, y22 = cy + dx;
+        int x11 = cx - dx, x12 = cx + dx, x21 = cx - dy, x22 = cx + dy;
+        if (x11 < pl.W && x12 >= 0 && y21 < pl.H && y22 >= 0) {
+            if (x11 < 0) x11 = 0;
+            if (x12 > pl.W - 1) x12 = pl.W - 1;
+            int sub = (g.lane + g.n - (it * 4) % g.n) % g.n; // rotate the work over the lanes
+            if ((g.n == 1 || sub == 0) && (unsigned)y11 < (unsigned)pl.H) tc_hline(pl, y11, x11, x12);
+            if ((g.n == 1 || sub == 1) && (unsigned)y12 < (unsigned)pl.H) tc_hline(pl, y12, x11, x12);
+            if (x21 < pl.W && x22 >= 0) {
+                if (x21 < 0) x21 = 0;
+                if (x22 > pl.W - 1) x22 = pl.W - 1;
+                if ((g.n == 1 || sub == 2) && (unsigned)y21 < (unsigned)pl.H) tc_hline(pl, y21, x21, x22);
+                if ((g.n == 1 || sub == 3) && (unsigned)y22 < (unsigned)pl.H) tc_hline(pl, y22, x21, x22);
+            }
+        }
+        dy++;
+        err += plus;
+        plus += 2;
+        int mask = (err <= 0) - 1;
+        err -= minus & mask;
+        dx += mask;
+        minus -= mask & 2;
+        it++;
+    }
+}
+
+TC_HD int64_t tc_cv_round(double v) { return (int64_t)rint(v); } // round half to even
+
+// cv2.polylines(img, np.int32([[p0, p1]]), False, 255, t) into the bit plane
+TC_HD void tc_polyline2(const TcLanes &g, const TcPlane &pl, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int t) {
+    int64_t ax = x0, ay = y0, bx = x1, by = y1;
+    if (t > 1) {
+        ax += t; ay += t; bx += t; by += t;
+        if (!tc_clip_line((int64_t)pl.W + 2 * t, (int64_t)pl.H + 2 * t, ax, ay, bx, by)) return;
+        ax -= t; ay -= t; bx -= t; by -= t;
+    } else {
+        tc_line_bresenham(g, pl, ax, ay, bx, by);
+        return;
+    }
+    int64_t P0x = ax << TC_XY_SHIFT, P0y = ay << TC_XY_SHIFT, P1x = bx << TC_XY_SHIFT, P1y = by << TC_XY_SHIFT;
+    const double INV = 1.0 / TC_XY_ONE;
+    double dx = (double)(P0x - P1x) * INV, dy = (double)(P1y - P0y) * INV;
+    double r = dx * dx + dy * dy;
+    int odd = t & 1;
+    int64_t T = (int64_t)t << (TC_XY_SHIFT - 1);
+    if (fabs(r) > 2.220446049250313e-16) {
+        r = ((double)T + odd * TC_XY_ONE * 0.5) / sqrt(r);
+        int64_t dpx = tc_cv_round(dy * r), dpy = tc_cv_round(dx * r);
+        int64_t v[4][2] = {{P0x + dpx, P0y + dpy}, {P0x - dpx, P0y - dpy}, {P1x - dpx, P1y - dpy}, {P1x + dpx, P1y + dpy}};
+        tc_fill_convex_poly4(g, pl, v);
+    }
+    int rad = (int)((T + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT);
+    tc_circle_filled(g, pl, (int)((P0x + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT), (int)((P0y + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT), rad);
+    tc_circle_filled(g, pl, (int)((P1x + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT), (int)((P1y + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT), rad);
+}

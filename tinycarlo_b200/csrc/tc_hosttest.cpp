@@ -1,0 +1,157 @@
+// tc_hosttest.cpp — CPU-only TEST build of the kernel arithmetic (tc_core.cuh) with one lane per group.
+//
+// NOT part of the product: nothing under tinycarlo_b200/*.py loads this library. It exists so that the
+// node-parallel clip passes, the closed-form rasteriser and the tracking logic that the CUDA kernels run can be
+// checked against the oracle in a container without a GPU (tests/test_core_host.py). The glue below mirrors the
+// kernels in tc_kernels.cuh step by step (same pass order, same ping-pong flags), sequentially.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tc_core.cuh"
+#include "tc_pack.h"
+
+#define HT_API extern "C" __attribute__((visibility("default")))
+
+struct HtMap {
+    TcPacked pk;
+    std::vector<TcClassTables> cls;
+    std::vector<int32_t> edge_off;
+    int C, sumE;
+    uint8_t colors[TC_MAX_CLASSES * 3];
+};
+
+HT_API HtMap *ht_map_create(const TcMapDesc *map) {
+    HtMap *m = new HtMap();
+    std::string err = tc_pack_map(map, m->pk);
+    if (!err.empty()) { delete m; return nullptr; }
+    tc_class_views(map, m->pk, m->pk.blob.data(), m->pk.adj.data(), m->cls);
+    m->C = map->n_classes;
+    m->sumE = map->ll_edge_off[m->C];
+    m->edge_off.assign(map->ll_edge_off, map->ll_edge_off + m->C + 1);
+    memcpy(m->colors, map->ll_colors, (size_t)3 * m->C);
+    return m;
+}
+HT_API void ht_map_destroy(HtMap *m) { delete m; }
+
+// mirrors tc_track_kernel for n envs (mode 0 step / 1 reset)
+HT_API void ht_track(const HtMap *m, int n, int mode, int wrapped, double *sf, int32_t *si, const double *car, const double *cam,
+                     double *pose, const float *act_cc, const int32_t *act_man, const uint8_t *mask, const int32_t *spawn,
+                     double *info_f64, int32_t *nearest, uint8_t *terminated, uint8_t *truncated) {
+    TcTrackTables t = tc_track_tables(m->pk.blob.data(), m->pk.L);
+    TcLanes g = {0, 1};
+    const int C = m->C;
+    for (int env = 0; env < n; env++) {
+        const double *cp = car + (size_t)env * TC_CP_N;
+        TcCarState s;
+        bool trunc = false;
+        if (mode == 1) {
+            if (mask && !mask[env]) continue;
+            tc_load_state(sf + (size_t)env * TC_SF_N, si + (size_t)env * TC_SI_N, s);
+            if (!tc_car_reset(t, cp, s, spawn[env])) continue;
+        } else {
+            tc_load_state(sf + (size_t)env * TC_SF_N, si + (size_t)env * TC_SI_N, s);
+            double v = tc_np_clip((double)act_cc[2 * env], -1.0, 1.0), st = tc_np_clip((double)act_cc[2 * env + 1], -1.0, 1.0);
+            trunc = tc_car_step(g, t, cp, s, v, st, act_man[env]);
+        }
+        double dist[TC_MAX_CLASSES];
+        int near[TC_MAX_CLASSES];
+        TcInfo info = tc_get_info(g, t, cp, s, wrapped != 0, dist, near);
+        tc_store_state(sf + (size_t)env * TC_SF_N, si + (size_t)env * TC_SI_N, s);
+        tc_camera_pose(cam + (size_t)env * TC_CAM_N + TC_CAM_E, s.x, s.y, cos(s.rot), sin(s.rot), pose + (size_t)env * 12);
+        double *r = info_f64 + (size_t)env * (4 + C);
+        r[0] = info.cte; r[1] = info.heading; r[2] = info.velocity;
+        if (mode == 0) r[3] = info.reward;
+        for (int c = 0; c < C; c++) { r[4 + c] = dist[c]; nearest[(size_t)env * C + c] = near[c]; }
+        if (mode == 0) { terminated[env] = info.terminated; truncated[env] = trunc; }
+    }
+}
+
+// mirrors tc_project_kernel for one (env, class)
+static int ht_project_one(const TcClassTables &ct, const double *pose, const double *cam, int H, int W, int32_t *seg) {
+    int n = ct.n_nodes, m = ct.n_edges;
+    std::vector<double> Px(n + 1), Py(n + 1), Pz(n + 1);
+    std::vector<int32_t> ix(n + 1), iy(n + 1);
+    std::vector<uint8_t> fA(n + 1), fB(n + 1), rA(n + 1), rB(n + 1), vis(n + 1);
+    TcProjScratch sc = {Px.data(), Py.data(), Pz.data(), ix.data(), iy.data(), fA.data(), rA.data(), vis.data()};
+    double max_range = cam[TC_CAM_MAX_RANGE];
+    for (int v = 0; v < n; v++) {
+        tc_transform_node(pose, ct.nodes[2 * v], ct.nodes[2 * v + 1], Px[v], Py[v], Pz[v]);
+        fA[v] = Pz[v] < 0;
+    }
+    for (int v = 0; v < n; v++) fB[v] = fA[v] | (uint8_t)tc_clip_pass_node(ct, sc, fA.data(), v, true, -0.0000001);
+    for (int v = 0; v < n; v++) fA[v] = fB[v] | (uint8_t)tc_clip_pass_node(ct, sc, fB.data(), v, false, -0.0000001);
+    for (int v = 0; v < n; v++) rA[v] = Pz[v] > -max_range;
+    for (int v = 0; v < n; v++) rB[v] = rA[v] | (uint8_t)tc_clip_pass_node(ct, sc, rA.data(), v, true, -max_range);
+    for (int v = 0; v < n; v++) rA[v] = rB[v] | (uint8_t)tc_clip_pass_node(ct, sc, rB.data(), v, false, -max_range);
+    for (int v = 0; v < n; v++) {
+        double u, w;
+        tc_project(cam, Px[v], Py[v], Pz[v], u, w);
+        ix[v] = tc_np_int32(u);
+        iy[v] = tc_np_int32(w);
+        vis[v] = (u > 0 && u < W && w > 0 && w < H && fA[v] && rA[v]) ? 1 : 0;
+    }
+    int cnt = 0;
+    for (int e = 0; e < m; e++) {
+        int n0 = ct.edges[2 * e], n1 = ct.edges[2 * e + 1];
+        if (!(vis[n0] || vis[n1])) continue;
+        seg[4 * cnt] = ix[n0]; seg[4 * cnt + 1] = iy[n0]; seg[4 * cnt + 2] = ix[n1]; seg[4 * cnt + 3] = iy[n1];
+        cnt++;
+    }
+    return cnt;
+}
+
+// mirrors tc_project_kernel + tc_raster_*_kernel (bands included) for n envs
+HT_API void ht_render(const HtMap *m, int n, int H, int W, int fmt, int rows_per_band, const double *pose, const double *cam,
+                      const int32_t *thickness, const uint8_t *mask, uint8_t *obs, int32_t *seg_count, int32_t *seg) {
+    const int C = m->C;
+    TcLanes g = {0, 1};
+    if (rows_per_band <= 0) rows_per_band = H;
+    const int n_bands = (H + rows_per_band - 1) / rows_per_band;
+    const int plane_words = (int)(((size_t)rows_per_band * W + 31) / 32) + 1;
+    for (int env = 0; env < n; env++) {
+        if (mask && !mask[env]) continue;
+        for (int c = 0; c < C; c++)
+            seg_count[(size_t)env * C + c] = ht_project_one(m->cls[c], pose + (size_t)env * 12, cam + (size_t)env * TC_CAM_N, H, W,
+                                                            seg + ((size_t)env * m->sumE + m->edge_off[c]) * 4);
+        if (!obs) continue;
+        for (int band = 0; band < n_bands; band++) {
+            int y_lo = band * rows_per_band, y_hi = y_lo + rows_per_band < H ? y_lo + rows_per_band : H;
+            std::vector<uint32_t> planes((size_t)C * plane_words, 0);
+            for (int c = 0; c < C; c++) {
+                TcPlane pl = {planes.data() + (size_t)c * plane_words, H, W, y_lo, y_hi};
+                const int32_t *s = seg + ((size_t)env * m->sumE + m->edge_off[c]) * 4;
+                for (int k = 0; k < seg_count[(size_t)env * C + c]; k++) tc_polyline2(g, pl, s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3], thickness[env]);
+            }
+            size_t npx = (size_t)(y_hi - y_lo) * W;
+            for (size_t p = 0; p < npx; p++) {
+                if (fmt == TC_OBS_CLASSES) {
+                    for (int c = 0; c < C; c++)
+                        obs[(((size_t)env * C + c) * H + y_lo) * W + p] = ((planes[(size_t)c * plane_words + (p >> 5)] >> (p & 31)) & 1) ? 255 : 0;
+                } else {
+                    uint8_t *o = obs + (((size_t)env * H + y_lo) * W + p) * 3;
+                    o[0] = o[1] = o[2] = 0;
+                    for (int c = 0; c < C; c++)
+                        if ((planes[(size_t)c * plane_words + (p >> 5)] >> (p & 31)) & 1) memcpy(o, m->colors + 3 * c, 3);
+                }
+            }
+        }
+    }
+}
+
+// one polyline into a byte image through the bit-plane rasteriser (fuzzed against cv2 / the oracle)
+// nlanes > 1 replays the work split of a warp lane by lane (lanes only interact through ORs into the plane)
+HT_API void ht_polyline(uint8_t *img, int H, int W, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int thickness, int y_lo, int y_hi,
+                        int nlanes) {
+    if (y_hi <= 0) { y_lo = 0; y_hi = H; }
+    if (nlanes <= 0) nlanes = 1;
+    std::vector<uint32_t> plane(((size_t)(y_hi - y_lo) * W + 31) / 32 + 1, 0);
+    TcPlane pl = {plane.data(), H, W, y_lo, y_hi};
+    for (int lane = 0; lane < nlanes; lane++) {
+        TcLanes g = {lane, nlanes};
+        tc_polyline2(g, pl, x0, y0, x1, y1, thickness);
+    }
+    for (size_t p = 0; p < (size_t)(y_hi - y_lo) * W; p++)
+        if ((plane[p >> 5] >> (p & 31)) & 1) img[(size_t)y_lo * W + p] = 255;
+}

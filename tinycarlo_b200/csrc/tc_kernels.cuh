@@ -1,0 +1,440 @@
+// tc_kernels.cuh — sm_100a kernels of the hot path. Included by tc_api.cu only.
+//
+//   tc_track_kernel     a warp per env: bicycle step, local-path selection, CTE / heading / laneline distances,
+//                       reward, pose for the camera. Map tables are staged once per block into shared memory with a
+//                       1-D TMA bulk copy (cp.async.bulk + mbarrier) and shared by the block's 8 envs.
+//   tc_project_kernel   a block per (env, class): transform the class's nodes, the four ordered clip passes in
+//                       node-parallel form, projection, endpoint culling, ordered compaction of the kept segments.
+//   tc_raster_kernel    a block per (env, plane band): OpenCV-exact rasterisation of the kept segments into a 1-bit
+//                       plane in shared memory, then bits -> bytes with 128-bit streaming stores; every output byte is
+//                       written exactly once. Classes: one plane per block. RGB: C planes + painter's-order compose.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "tc_core.cuh"
+
+#define TC_TRACK_THREADS 256
+#define TC_PROJ_THREADS 128
+#define TC_RASTER_THREADS 256
+
+// ------------------------------------------------------------------------------------------------ TMA / mbarrier PTX
+__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(tc_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(tc_smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// 128-bit streaming store (evict-first: the observation is consumed by a later kernel, never re-read here)
+__device__ __forceinline__ void tc_st_cs(void *p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ tracking
+struct TcTrackArgs {
+    const unsigned char *blob; // packed map tables (global)
+    TcBlobLayout layout;
+    int n_envs;
+    int mode;     // 0 = step, 1 = reset
+    int wrapped;
+    double *sf;
+    int32_t *si;
+    const double *car;   // [N, TC_CP_N]
+    const double *cam;   // [N, TC_CAM_N]
+    double *pose;        // [N, 12] out
+    const float *act_cc; // [N,2]
+    const int32_t *act_man;
+    const uint8_t *mask;        // reset: envs to reset (NULL = all)
+    const int32_t *spawn_nodes; // reset
+    TcOutputs out;
+};
+
+__global__ void __launch_bounds__(TC_TRACK_THREADS) tc_track_kernel(const TcTrackArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_blob[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        tc_mbar_init(&bar, 1);
+        tc_fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc_mbar_expect_tx(&bar, (uint32_t)a.layout.total_bytes);
+        tc_bulk_g2s(smem_blob, a.blob, (uint32_t)a.layout.total_bytes, &bar);
+    }
+    const int warp = threadIdx.x >> 5;
+    const int env = blockIdx.x * (TC_TRACK_THREADS / 32) + warp;
+    TcLanes g = {(int)(threadIdx.x & 31), 32};
+    tc_mbar_wait(&bar, 0);
+    if (env >= a.n_envs) return;
+    const TcTrackTables t = tc_track_tables(smem_blob, a.layout);
+    const int C = t.n_classes;
+    const double *cp = a.car + (size_t)env * TC_CP_N;
+    double *sf = a.sf + (size_t)env * TC_SF_N;
+    int32_t *si = a.si + (size_t)env * TC_SI_N;
+    TcCarState s;
+    bool truncated = false;
+    if (a.mode == 1) {
+        if (a.mask && !a.mask[env]) return;
+        tc_load_state(sf, si, s);
+        if (!tc_car_reset(t, cp, s, a.spawn_nodes[env])) return;
+    } else {
+        tc_load_state(sf, si, s);
+        // env.py:118: np.clip(action["car_control"], -1, 1) on float64
+        double v_cmd = tc_np_clip((double)a.act_cc[2 * env], -1.0, 1.0), s_cmd = tc_np_clip((double)a.act_cc[2 * env + 1], -1.0, 1.0);
+        truncated = tc_car_step(g, t, cp, s, v_cmd, s_cmd, a.act_man[env]);
+    }
+    double dist[TC_MAX_CLASSES];
+    int nearest[TC_MAX_CLASSES];
+    TcInfo info = tc_get_info(g, t, cp, s, a.wrapped != 0, dist, nearest);
+    if (g.lane != 0) return;
+    tc_store_state(sf, si, s);
+    // pose for the camera pass: front-axle update already evaluated cos/sin(rot); recomputing keeps the code simple
+    tc_camera_pose(a.cam + (size_t)env * TC_CAM_N + TC_CAM_E, s.x, s.y, cos(s.rot), sin(s.rot), a.pose + (size_t)env * 12);
+    const TcOutputs &o = a.out;
+    if (o.cte) o.cte[env] = (float)info.cte;
+    if (o.heading_error) o.heading_error[env] = (float)info.heading;
+    if (o.velocity) o.velocity[env] = (float)info.velocity;
+    if (o.position) { o.position[2 * env] = (float)s.x; o.position[2 * env + 1] = (float)s.y; }
+    if (o.orientation) o.orientation[env] = (float)s.rot;
+    if (o.laneline_distances) for (int c = 0; c < C; c++) o.laneline_distances[(size_t)env * C + c] = (float)dist[c];
+    if (o.nearest_edge) for (int c = 0; c < C; c++) o.nearest_edge[(size_t)env * C + c] = nearest[c];
+    // car.py:66 builds local_path coordinates only when the info is non-empty (len >= 2)
+    int plen = s.path_len >= 2 ? s.path_len : 0;
+    if (o.local_path)
+        for (int i = 0; i < 4; i++) {
+            bool ok = i < plen;
+            o.local_path[(size_t)env * 8 + 2 * i] = ok ? (float)t.lp_nodes[2 * s.pn[2 * i + 1]] : 0.0f;
+            o.local_path[(size_t)env * 8 + 2 * i + 1] = ok ? (float)t.lp_nodes[2 * s.pn[2 * i + 1] + 1] : 0.0f;
+        }
+    if (o.local_path_nodes)
+        for (int i = 0; i < 8; i++) o.local_path_nodes[(size_t)env * 8 + i] = (i >> 1) < s.path_len ? s.pn[i] : -1;
+    if (o.path_len) o.path_len[env] = s.path_len;
+    if (o.info_f64) {
+        double *r = o.info_f64 + (size_t)env * (4 + C);
+        r[TC_INFO_CTE] = info.cte; r[TC_INFO_HEADING] = info.heading; r[TC_INFO_VELOCITY] = info.velocity;
+        if (a.mode == 0) r[TC_INFO_REWARD] = info.reward;
+        for (int c = 0; c < C; c++) r[TC_INFO_DIST0 + c] = dist[c];
+    }
+    if (a.mode == 0) {
+        if (o.reward) o.reward[env] = (float)info.reward;
+        if (o.terminated) o.terminated[env] = info.terminated ? 1 : 0;
+        if (o.truncated) o.truncated[env] = truncated ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ camera pass
+struct TcProjArgs {
+    const TcClassTables *classes; // [C] device array
+    int n_envs, n_classes, sum_edges, max_nodes;
+    int H, W;
+    const int32_t *edge_off; // [C+1] device
+    const double *pose;      // [N,12]
+    const double *cam;       // [N,TC_CAM_N]
+    const uint8_t *mask;     // optional
+    int32_t *seg;            // [N, sumE, 4]
+    int32_t *seg_count;      // [N, C]
+};
+
+__host__ __device__ inline size_t tc_proj_smem_bytes(int max_nodes) {
+    size_t n = (size_t)((max_nodes + 15) & ~15);
+    return n * (3 * sizeof(double) + 2 * sizeof(int32_t) + 5);
+}
+
+__global__ void __launch_bounds__(TC_PROJ_THREADS) tc_project_kernel(const TcProjArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int warp_cnt[TC_PROJ_THREADS / 32];
+    __shared__ int base_cnt;
+    const int env = blockIdx.x / a.n_classes, c = blockIdx.x % a.n_classes;
+    if (a.mask && !a.mask[env]) return;
+    const TcClassTables ct = a.classes[c];
+    const int n = ct.n_nodes, m = ct.n_edges;
+    const size_t np = (size_t)((a.max_nodes + 15) & ~15);
+    TcProjScratch sc;
+    sc.Px = (double *)smem_raw; sc.Py = sc.Px + np; sc.Pz = sc.Py + np;
+    sc.ix = (int32_t *)(sc.Pz + np); sc.iy = sc.ix + np;
+    uint8_t *fA = (uint8_t *)(sc.iy + np), *fB = fA + np, *rA = fB + np, *rB = rA + np;
+    sc.vis = rB + np;
+    sc.front = fA; sc.inr = rA;
+    const int tid = threadIdx.x;
+    double pose[12], cam[TC_CAM_N];
+#pragma unroll
+    for (int i = 0; i < 12; i++) pose[i] = a.pose[(size_t)env * 12 + i];
+#pragma unroll
+    for (int i = TC_CAM_FX; i <= TC_CAM_MAX_RANGE; i++) cam[i] = a.cam[(size_t)env * TC_CAM_N + i];
+    const double max_range = cam[TC_CAM_MAX_RANGE];
+
+    for (int v = tid; v < n; v += TC_PROJ_THREADS) {
+        double X, Y, Z;
+        tc_transform_node(pose, ct.nodes[2 * v], ct.nodes[2 * v + 1], X, Y, Z);
+        sc.Px[v] = X; sc.Py[v] = Y; sc.Pz[v] = Z;
+        fA[v] = Z < 0;
+    }
+    __syncthreads();
+    // camera.py:70-77 near-plane fix-ups
+    for (int v = tid; v < n; v += TC_PROJ_THREADS) fB[v] = fA[v] | (uint8_t)tc_clip_pass_node(ct, sc, fA, v, true, -0.0000001);
+    __syncthreads();
+    for (int v = tid; v < n; v += TC_PROJ_THREADS) fA[v] = fB[v] | (uint8_t)tc_clip_pass_node(ct, sc, fB, v, false, -0.0000001);
+    __syncthreads();
+    // camera.py:80-86 range fix-ups (depths is a live view: evaluated on the moved z)
+    for (int v = tid; v < n; v += TC_PROJ_THREADS) rA[v] = sc.Pz[v] > -max_range;
+    __syncthreads();
+    for (int v = tid; v < n; v += TC_PROJ_THREADS) rB[v] = rA[v] | (uint8_t)tc_clip_pass_node(ct, sc, rA, v, true, -max_range);
+    __syncthreads();
+    for (int v = tid; v < n; v += TC_PROJ_THREADS) rA[v] = rB[v] | (uint8_t)tc_clip_pass_node(ct, sc, rB, v, false, -max_range);
+    __syncthreads();
+    // camera.py:89-93 projection and node visibility
+    for (int v = tid; v < n; v += TC_PROJ_THREADS) {
+        double u, w;
+        tc_project(cam, sc.Px[v], sc.Py[v], sc.Pz[v], u, w);
+        sc.ix[v] = tc_np_int32(u);
+        sc.iy[v] = tc_np_int32(w);
+        sc.vis[v] = (u > 0 && u < a.W && w > 0 && w < a.H && fA[v] && rA[v]) ? 1 : 0;
+    }
+    if (tid == 0) base_cnt = 0;
+    __syncthreads();
+    // camera.py:95: keep edges with >= 1 visible endpoint, in edge order (ordered block compaction)
+    int32_t *seg = a.seg + ((size_t)env * a.sum_edges + a.edge_off[c]) * 4;
+    for (int e0 = 0; e0 < m; e0 += TC_PROJ_THREADS) {
+        int e = e0 + tid;
+        int n0 = 0, n1 = 0;
+        bool keep = false;
+        if (e < m) {
+            n0 = ct.edges[2 * e]; n1 = ct.edges[2 * e + 1];
+            keep = sc.vis[n0] || sc.vis[n1];
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if ((tid & 31) == 0) warp_cnt[tid >> 5] = __popc(bal);
+        __syncthreads();
+        int pos = base_cnt + __popc(bal & ((1u << (tid & 31)) - 1));
+        for (int w = 0; w < (tid >> 5); w++) pos += warp_cnt[w];
+        if (keep) {
+            int4 s4 = make_int4(sc.ix[n0], sc.iy[n0], sc.ix[n1], sc.iy[n1]);
+            *(int4 *)(seg + 4 * pos) = s4;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < TC_PROJ_THREADS / 32; w++) tot += warp_cnt[w];
+            base_cnt += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) a.seg_count[(size_t)env * a.n_classes + c] = base_cnt;
+}
+
+// ------------------------------------------------------------------------------------------------ rasterise + store
+struct TcRasterArgs {
+    int n_envs, n_classes, sum_edges;
+    int H, W;
+    int rows_per_band, n_bands;
+    int plane_words; // 32-bit words of one band plane (incl. one pad word)
+    const int32_t *edge_off;   // [C+1] device
+    const int32_t *thickness;  // [N]
+    const uint8_t *mask;       // optional
+    const int32_t *seg;        // [N, sumE, 4]
+    const int32_t *seg_count;  // [N, C]
+    uint8_t *obs;
+    uint8_t colors[TC_MAX_CLASSES * 3];
+};
+
+// 16 bits of the plane starting at bit offset o (plane has a pad word, so reading word+1 is always in bounds)
+__device__ __forceinline__ uint32_t tc_bits16(const uint32_t *plane, uint32_t o) {
+    uint32_t w = o >> 5;
+    return __funnelshift_r(plane[w], plane[w + 1], o & 31) & 0xffffu;
+}
+// 4 bits -> 4 bytes of 0x00 / 0xFF
+__device__ __forceinline__ uint32_t tc_expand4(uint32_t b) { return (((b & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu; }
+__device__ __forceinline__ uint4 tc_expand16(uint32_t b) {
+    return make_uint4(tc_expand4(b), tc_expand4(b >> 4), tc_expand4(b >> 8), tc_expand4(b >> 12));
+}
+
+// Stream `nbytes` bytes of 0/255 to `out` from the bit plane (bit i <-> byte i). `any` false: plane is known empty.
+__device__ __forceinline__ void tc_store_plane(uint8_t *out, size_t nbytes, const uint32_t *plane, bool any) {
+    const int tid = threadIdx.x;
+    size_t head = (16 - ((uintptr_t)out & 15)) & 15;
+    if (head > nbytes) head = nbytes;
+    for (size_t i = tid; i < head; i += TC_RASTER_THREADS) out[i] = (any && ((plane[i >> 5] >> (i & 31)) & 1)) ? 255 : 0;
+    const size_t nvec = (nbytes - head) >> 4;
+    uint4 *o4 = (uint4 *)(out + head);
+    if (!any) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        size_t j = tid;
+        for (; j + 3 * TC_RASTER_THREADS < nvec; j += 4 * TC_RASTER_THREADS) {
+            tc_st_cs(o4 + j, z);
+            tc_st_cs(o4 + j + TC_RASTER_THREADS, z);
+            tc_st_cs(o4 + j + 2 * TC_RASTER_THREADS, z);
+            tc_st_cs(o4 + j + 3 * TC_RASTER_THREADS, z);
+        }
+        for (; j < nvec; j += TC_RASTER_THREADS) tc_st_cs(o4 + j, z);
+    } else {
+        size_t j = tid;
+        for (; j + 3 * TC_RASTER_THREADS < nvec; j += 4 * TC_RASTER_THREADS) {
+            uint32_t b0 = tc_bits16(plane, (uint32_t)(head + 16 * j));
+            uint32_t b1 = tc_bits16(plane, (uint32_t)(head + 16 * (j + TC_RASTER_THREADS)));
+            uint32_t b2 = tc_bits16(plane, (uint32_t)(head + 16 * (j + 2 * TC_RASTER_THREADS)));
+            uint32_t b3 = tc_bits16(plane, (uint32_t)(head + 16 * (j + 3 * TC_RASTER_THREADS)));
+            tc_st_cs(o4 + j, tc_expand16(b0));
+            tc_st_cs(o4 + j + TC_RASTER_THREADS, tc_expand16(b1));
+            tc_st_cs(o4 + j + 2 * TC_RASTER_THREADS, tc_expand16(b2));
+            tc_st_cs(o4 + j + 3 * TC_RASTER_THREADS, tc_expand16(b3));
+        }
+        for (; j < nvec; j += TC_RASTER_THREADS) tc_st_cs(o4 + j, tc_expand16(tc_bits16(plane, (uint32_t)(head + 16 * j))));
+    }
+    for (size_t i = head + (nvec << 4) + tid; i < nbytes; i += TC_RASTER_THREADS)
+        out[i] = (any && ((plane[i >> 5] >> (i & 31)) & 1)) ? 255 : 0;
+}
+
+// classes: grid = N*C*n_bands blocks; each owns rows [y_lo, y_hi) of one class plane
+__global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_classes_kernel(const TcRasterArgs a) {
+    extern __shared__ __align__(16) uint32_t plane[];
+    const int band = blockIdx.x % a.n_bands;
+    const int pc = blockIdx.x / a.n_bands;
+    const int env = pc / a.n_classes, c = pc % a.n_classes;
+    if (a.mask && !a.mask[env]) return;
+    const int y_lo = band * a.rows_per_band;
+    const int y_hi = min(a.H, y_lo + a.rows_per_band);
+    const int cnt = a.seg_count[(size_t)env * a.n_classes + c];
+    uint8_t *out = a.obs + (((size_t)env * a.n_classes + c) * a.H + y_lo) * a.W;
+    const size_t nbytes = (size_t)(y_hi - y_lo) * a.W;
+    if (cnt > 0) {
+        for (int i = threadIdx.x; i < a.plane_words; i += TC_RASTER_THREADS) plane[i] = 0;
+        __syncthreads();
+        const int32_t *seg = a.seg + ((size_t)env * a.sum_edges + a.edge_off[c]) * 4;
+        const int t = a.thickness[env];
+        TcPlane pl = {plane, a.H, a.W, y_lo, y_hi};
+        TcLanes g = {(int)(threadIdx.x & 31), 32};
+        for (int k = threadIdx.x >> 5; k < cnt; k += TC_RASTER_THREADS / 32) {
+            int4 s4 = *(const int4 *)(seg + 4 * k);
+            tc_polyline2(g, pl, s4.x, s4.y, s4.z, s4.w, t);
+        }
+        __syncthreads();
+    }
+    tc_store_plane(out, nbytes, plane, cnt > 0);
+}
+
+// rgb: grid = N*n_bands blocks; C class planes + an "any" plane; later classes overwrite earlier ones (renderer.py:41-43)
+__global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const TcRasterArgs a) {
+    extern __shared__ __align__(16) uint32_t planes[];
+    const int band = blockIdx.x % a.n_bands;
+    const int env = blockIdx.x / a.n_bands;
+    if (a.mask && !a.mask[env]) return;
+    const int C = a.n_classes;
+    const int y_lo = band * a.rows_per_band;
+    const int y_hi = min(a.H, y_lo + a.rows_per_band);
+    uint8_t *out = a.obs + ((size_t)env * a.H + y_lo) * a.W * 3;
+    const size_t nbytes = (size_t)(y_hi - y_lo) * a.W * 3;
+    int total = 0;
+    for (int c = 0; c < C; c++) total += a.seg_count[(size_t)env * C + c];
+    uint32_t *anyp = planes + (size_t)C * a.plane_words;
+    if (total > 0) {
+        for (int i = threadIdx.x; i < (C + 1) * a.plane_words; i += TC_RASTER_THREADS) planes[i] = 0;
+        __syncthreads();
+        const int t = a.thickness[env];
+        TcLanes g = {(int)(threadIdx.x & 31), 32};
+        int k0 = 0;
+        for (int c = 0; c < C; c++) {
+            const int cnt = a.seg_count[(size_t)env * C + c];
+            const int32_t *seg = a.seg + ((size_t)env * a.sum_edges + a.edge_off[c]) * 4;
+            TcPlane pl = {planes + (size_t)c * a.plane_words, a.H, a.W, y_lo, y_hi};
+            // warps take segments round-robin across all classes
+            for (int k = 0; k < cnt; k++, k0++)
+                if ((k0 & (TC_RASTER_THREADS / 32 - 1)) == (int)(threadIdx.x >> 5)) {
+                    int4 s4 = *(const int4 *)(seg + 4 * k);
+                    tc_polyline2(g, pl, s4.x, s4.y, s4.z, s4.w, t);
+                }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.plane_words; i += TC_RASTER_THREADS) {
+            uint32_t o = 0;
+            for (int c = 0; c < C; c++) o |= planes[(size_t)c * a.plane_words + i];
+            anyp[i] = o;
+        }
+        __syncthreads();
+    }
+    // byte stream: byte q belongs to pixel q/3, channel q%3
+    size_t head = (16 - ((uintptr_t)out & 15)) & 15;
+    if (head > nbytes) head = nbytes;
+    auto byte_at = [&](size_t q) -> uint8_t {
+        if (total == 0) return 0;
+        size_t p = q / 3;
+        int ch = (int)(q - 3 * p);
+        uint8_t v = 0;
+        for (int c = 0; c < C; c++)
+            if ((planes[(size_t)c * a.plane_words + (p >> 5)] >> (p & 31)) & 1) v = a.colors[3 * c + ch];
+        return v;
+    };
+    for (size_t i = threadIdx.x; i < head; i += TC_RASTER_THREADS) out[i] = byte_at(i);
+    const size_t nvec = (nbytes - head) >> 4;
+    uint4 *o4 = (uint4 *)(out + head);
+    for (size_t j = threadIdx.x; j < nvec; j += TC_RASTER_THREADS) {
+        size_t q0 = head + 16 * j;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (total > 0) {
+            // pixels q0/3 .. (q0+15)/3: at most 6 pixels -> 6 bits of the "any" plane
+            uint32_t p0 = (uint32_t)(q0 / 3);
+            uint32_t w = p0 >> 5;
+            uint32_t bits = __funnelshift_r(anyp[w], anyp[w + 1], p0 & 31) & 0x3fu;
+            if (bits) {
+                uint32_t r[4] = {0, 0, 0, 0};
+                for (int k = 0; k < 16; k++) r[k >> 2] |= (uint32_t)byte_at(q0 + k) << (8 * (k & 3));
+                v = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+        }
+        tc_st_cs(o4 + j, v);
+    }
+    for (size_t i = head + (nvec << 4) + threadIdx.x; i < nbytes; i += TC_RASTER_THREADS) out[i] = byte_at(i);
+}
+
+// ------------------------------------------------------------------------------------------------ test hook
+// layer.py known-answer queries on class 0 (tests only)
+__global__ void tc_debug_layer_kernel(const unsigned char *blob, TcBlobLayout L, int op, double px, double py, double ang, int i0, int i1,
+                                      int32_t *out_i, double *out_d) {
+    TcTrackTables t = tc_track_tables(blob, L);
+    TcLanes g = {(int)(threadIdx.x & 31), 32};
+    const double *nodes = t.ll_nodes;
+    const int32_t *edges = t.ll_edges;
+    int m = t.ll_edge_off[1] - t.ll_edge_off[0];
+    int ri = 0;
+    double rd = 0;
+    if (op == 0) ri = tc_nearest_edge(g, nodes, edges, m, px, py, nullptr, 0, 0);
+    else if (op == 1) {
+        // orientation of laneline edges is not tabulated; compute it into a small local table via atan2 on the device
+        int best = -1;
+        double bd = 0;
+        for (int e = g.lane; e < m; e += g.n) {
+            int a = edges[2 * e], b = edges[2 * e + 1];
+            double o = atan2(nodes[2 * b + 1] - nodes[2 * a + 1], nodes[2 * b] - nodes[2 * a]);
+            if (!(fabs(tc_clip_angle(o - ang)) <= 30.0 * (TC_PI / 180.0))) continue;
+            double d = fabs(tc_dist(px, py, nodes[2 * a], nodes[2 * a + 1]) + tc_dist(px, py, nodes[2 * b], nodes[2 * b + 1]));
+            if (best < 0 || d < bd) { best = e; bd = d; }
+        }
+        tc_group_argmin(g, bd, best);
+        ri = best;
+    } else if (op == 2)
+        ri = tc_within_edge_bounds(px, py, nodes[2 * i0], nodes[2 * i0 + 1], nodes[2 * i1], nodes[2 * i1 + 1]) ? 1 : 0;
+    else if (op == 3)
+        rd = tc_distance_to_edge(px, py, nodes[2 * i0], nodes[2 * i0 + 1], nodes[2 * i1], nodes[2 * i1 + 1]);
+    else if (op == 4)
+        rd = tc_clip_angle(ang);
+    if (threadIdx.x == 0) {
+        out_i[0] = ri;
+        out_d[0] = rd;
+    }
+}

@@ -1,0 +1,334 @@
+"""TinyCarloVecEnv — N tinycarlo environments stepped in lockstep on one B200, CUDA tensors in and out.
+
+The vectorised counterpart of the reference's TinyCarloEnv (tinycarlo/env.py:15-147): same config schema, same action
+dict ({"car_control": [velocity cmd, steering cmd] in [-1,1], "maneuver": 0..3}), same observation formats and the
+same info keys, batched along dim 0. One step() enqueues three hand-written sm_100a kernels through the C ABI
+(tracking, camera pass, rasterise+store) on torch's current stream and returns views of preallocated tensors; there
+is no host synchronisation inside step() and no CPU implementation.
+
+Returned tensors are owned by the env and are overwritten by the next step()/reset(); clone what must survive.
+"""
+import ctypes as C
+from typing import Any, Dict, Optional, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .camera_params import camera_row
+from .config import camera_params, car_param_row, load_config, resolve_map_path, sim_params
+from .maptables import MapTables
+from .spawn import SpawnSampler
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class TinyCarloVecEnv:
+    is_vector_env = True
+
+    def __init__(self, config: Union[str, Dict[str, Any]], num_envs: int, device: Union[str, int, torch.device] = "cuda",
+                 obs_format: Optional[str] = None, env_index_offset: int = 0, spawn_table_len: int = 16, debug_segments: bool = False):
+        """config: yaml path / directory / dict as for the reference env. num_envs: envs on THIS device.
+        env_index_offset: global index of local env 0 (multi-GPU sharding: env i is seeded with seed + offset + i, so
+        results do not depend on how the envs are sharded). debug_segments: also export the projected int32 segments."""
+        if not torch.cuda.is_available():
+            raise _lib.TinyCarloError("TinyCarloVecEnv needs a CUDA device: there is no CPU implementation")
+        self.config, self.config_path = load_config(config)
+        sp = sim_params(self.config)
+        self.fps, self.T = sp["fps"], sp["T"]
+        self.observation_space_format = obs_format or sp["observation_space_format"]
+        self.map = MapTables(resolve_map_path(self.config["map"], self.config_path), self.config["map"]["pixel_per_meter"],
+                             self.config["map"].get("spawn_points", None))
+        self.cam_cfg = camera_params(self.config["camera"])
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.env_index_offset = int(env_index_offset)
+        self.H, self.W = (int(v) for v in self.cam_cfg["resolution"])
+        self.n_classes = self.map.n_classes
+        self.class_names = self.map.get_laneline_names()
+        self.track_width = float(self.config["car"].get("track_width", 0.03))
+        self.wrapped = False
+        self.no_observation = False
+        N, Cn = self.num_envs, self.n_classes
+        dev = self.device
+        fmt = _lib.TC_OBS_CLASSES if self.observation_space_format != "rgb" else _lib.TC_OBS_RGB
+        self._fmt = fmt
+        self.obs_shape = (Cn, self.H, self.W) if fmt == _lib.TC_OBS_CLASSES else (self.H, self.W, 3)
+
+        # ---- library handle (map tables go to the device once)
+        m = self.map
+        self._keep = [np.ascontiguousarray(a) for a in (m.ll_node_off, m.ll_edge_off, m.ll_nodes, m.ll_edges, m.colors, m.lp_nodes,
+                                                        m.lp_edges, m.lp_orient, m.lp_orient_rev)]
+        k = self._keep
+        desc = _lib.TcMapDesc(Cn, k[0].ctypes.data, k[1].ctypes.data, k[2].ctypes.data, k[3].ctypes.data, k[4].ctypes.data,
+                              len(m.lp_nodes), len(m.lp_edges), k[5].ctypes.data, k[6].ctypes.data, k[7].ctypes.data, k[8].ctypes.data)
+        sim = _lib.TcSimDesc(self.H, self.W, fmt)
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(self._L.tc_create(C.byref(desc), C.byref(sim), N, self.device.index, C.byref(h)), "tc_create")
+        self._h = h
+
+        # ---- outputs (allocated once; step()/reset() return views)
+        with torch.cuda.device(dev):
+            self.obs = torch.zeros((N,) + self.obs_shape, dtype=torch.uint8, device=dev)
+            f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+            self.out = {"cte": f32(N), "heading_error": f32(N), "velocity": f32(N), "reward": f32(N), "position": f32(N, 2),
+                        "orientation": f32(N), "laneline_distances": f32(N, Cn),
+                        "nearest_edge": torch.full((N, Cn), -1, dtype=torch.int32, device=dev), "local_path": f32(N, 4, 2),
+                        "local_path_nodes": torch.full((N, 4, 2), -1, dtype=torch.int32, device=dev),
+                        "path_len": torch.zeros(N, dtype=torch.int32, device=dev),
+                        "terminated": torch.zeros(N, dtype=torch.uint8, device=dev),
+                        "truncated": torch.zeros(N, dtype=torch.uint8, device=dev),
+                        "info_f64": torch.zeros((N, 4 + Cn), dtype=torch.float64, device=dev)}
+            if debug_segments:
+                self.out["seg_count"] = torch.zeros((N, Cn), dtype=torch.int32, device=dev)
+                self.out["seg_i32"] = torch.zeros((N, max(int(m.ll_edge_off[-1]), 1), 4), dtype=torch.int32, device=dev)
+            self._spawn_nodes = torch.zeros(N, dtype=torch.int32, device=dev)
+            self._mask_all = torch.ones(N, dtype=torch.uint8, device=dev)
+        self._outs = self._make_outputs(with_obs=True)
+        self._outs_noobs = self._make_outputs(with_obs=False)
+
+        # ---- parameters
+        self._car_rows = np.tile(np.array(car_param_row(self.config["car"], self.T), np.float64), (N, 1))
+        cc = self.cam_cfg
+        self._cam_rows = np.tile(camera_row(cc["position"], cc["orientation"], cc["fov"], cc["resolution"], cc["max_range"]), (N, 1))
+        self._thickness = np.full(N, int(cc["line_thickness"]), np.int32)
+        self._upload_params()
+
+        # ---- spawn draws (map.py:51-69): per-env numpy Generators seeded like gymnasium, pre-drawn K resets ahead
+        self._K = int(spawn_table_len)
+        self._sampler = SpawnSampler(self.map, N, self._K, self.env_index_offset)
+        self._spawn_table = None   # device int32 [N, K]
+        self._spawn_cursor = None  # device int32 [N]
+        self._resets_since_refill = 0
+        self._seeded = False
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def _make_outputs(self, with_obs: bool) -> _lib.TcOutputs:
+        o = _lib.TcOutputs()
+        for name in _lib.OUTPUT_FIELDS:
+            t = self.obs if name == "obs" else self.out.get(name)
+            if name == "obs" and not with_obs:
+                t = None
+            setattr(o, name, None if t is None else t.data_ptr())
+        return o
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _upload_params(self):
+        with torch.cuda.device(self.device):
+            car = torch.from_numpy(self._car_rows).to(self.device)
+            cam = torch.from_numpy(self._cam_rows).to(self.device)
+            th = torch.from_numpy(self._thickness).to(self.device)
+            _lib.check(self._L.tc_set_car_params(self._h, _ptr(car), self._stream()), "tc_set_car_params")
+            _lib.check(self._L.tc_set_camera_params(self._h, _ptr(cam), _ptr(th), self._stream()), "tc_set_camera_params")
+            torch.cuda.current_stream(self.device).synchronize()  # the temporaries die here
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.tc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def set_wrapped(self, wrapped: bool = True):
+        """env.py:137-138: wrappers switch the default reward/termination off."""
+        self.wrapped = bool(wrapped)
+        _lib.check(self._L.tc_set_wrapped(self._h, int(self.wrapped)), "tc_set_wrapped")
+
+    def set_car_params(self, **kw):
+        """Per-env car parameters (domain randomisation). Each value: scalar or array [N]; None = unlimited where the
+        reference allows it (steering_speed, max_acceleration). Keys as in the config's `car` section."""
+        cols = {"wheelbase": 0, "track_width": 1, "max_velocity": 2, "max_steering_angle": 3, "steering_speed": 4,
+                "max_acceleration": 5, "max_deceleration": 6}
+        for key, val in kw.items():
+            col = cols[key]
+            if val is None:
+                self._car_rows[:, col] = np.nan
+            else:
+                v = val.detach().cpu().numpy() if isinstance(val, torch.Tensor) else np.asarray(val, np.float64)
+                self._car_rows[:, col] = v
+        self._upload_params()
+
+    def set_camera_params(self, position=None, orientation=None, fov=None, max_range=None, line_thickness=None, env_ids=None):
+        """Per-env camera parameters (camera.py:48-50 update_params, vectorised). Arrays are [n,3] / [n] for the envs in
+        env_ids (default: all), or a single value broadcast. E and K are rebuilt on the host with the reference's calls."""
+        ids = np.arange(self.num_envs) if env_ids is None else np.asarray(env_ids).reshape(-1)
+        n = len(ids)
+        if not hasattr(self, "_cam_src"):
+            cc = self.cam_cfg
+            self._cam_src = {"position": np.tile(np.asarray(cc["position"], np.float64), (self.num_envs, 1)),
+                             "orientation": np.tile(np.asarray(cc["orientation"], np.float64), (self.num_envs, 1)),
+                             "fov": np.full(self.num_envs, float(cc["fov"])), "max_range": np.full(self.num_envs, float(cc["max_range"]))}
+
+        def bc(v, shape):
+            v = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, np.float64)
+            return np.broadcast_to(v, shape)
+        if position is not None:
+            self._cam_src["position"][ids] = bc(position, (n, 3))
+        if orientation is not None:
+            self._cam_src["orientation"][ids] = bc(orientation, (n, 3))
+        if fov is not None:
+            self._cam_src["fov"][ids] = bc(fov, (n,))
+        if max_range is not None:
+            self._cam_src["max_range"][ids] = bc(max_range, (n,))
+        if line_thickness is not None:
+            self._thickness[ids] = bc(line_thickness, (n,)).astype(np.int32)
+        res = [self.H, self.W]
+        s = self._cam_src
+        cache = {}
+        for i in ids:
+            key = (tuple(s["position"][i]), tuple(s["orientation"][i]), float(s["fov"][i]), float(s["max_range"][i]))
+            row = cache.get(key)
+            if row is None:
+                row = cache[key] = camera_row(s["position"][i], s["orientation"][i], s["fov"][i], res, s["max_range"][i])
+            self._cam_rows[i] = row
+        self._upload_params()
+
+    def set_camera_rows(self, cam_rows: np.ndarray, line_thickness=None):
+        """Raw per-env camera rows [N,20] (E 3x4 row-major, fx, fy, cx, cy, max_range, pad) — include/tinycarlo_b200.h TC_CAM_*."""
+        self._cam_rows[:] = np.asarray(cam_rows, np.float64).reshape(self.num_envs, _lib.TC_CAM_N)
+        if line_thickness is not None:
+            self._thickness[:] = np.asarray(line_thickness, np.int32)
+        self._upload_params()
+
+    # ------------------------------------------------------------------------------------------------ spawn draws
+    def _seed(self, seed: Optional[int]):
+        tab = self._sampler.seed(seed)
+        self._upload_spawn_table(tab)
+        self._seeded = True
+
+    def _upload_spawn_table(self, tab: np.ndarray):
+        with torch.cuda.device(self.device):
+            self._spawn_table = torch.from_numpy(tab).to(self.device)
+            self._spawn_cursor = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._resets_since_refill = 0
+
+    # ------------------------------------------------------------------------------------------------ gym-like API
+    def _info(self) -> Dict[str, torch.Tensor]:
+        o = self.out
+        return {"cte": o["cte"], "heading_error": o["heading_error"], "position": o["position"], "orientation": o["orientation"],
+                "laneline_distances": o["laneline_distances"], "local_path": o["local_path"], "velocity": o["velocity"],
+                "nearest_edge": o["nearest_edge"], "local_path_nodes": o["local_path_nodes"], "path_len": o["path_len"]}
+
+    def reset(self, seed: Optional[int] = None, mask: Optional[torch.Tensor] = None, spawn_nodes: Optional[torch.Tensor] = None):
+        """env.py:101-113 for the envs selected by `mask` (bool/uint8 [N]; None = all). seed re-seeds every env's spawn
+        generator (env i gets seed + env_index_offset + i, as gymnasium.vector does). spawn_nodes (int32 [N]) overrides
+        the draw (tests). Returns (obs, info); info of reset envs is the reference's empty info (zeros)."""
+        with torch.cuda.device(self.device):
+            if seed is not None or not self._seeded:
+                self._seed(seed)
+            if mask is not None:
+                mask_u8 = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            else:
+                mask_u8 = self._mask_all
+            if spawn_nodes is not None:
+                nodes = spawn_nodes.to(device=self.device, dtype=torch.int32).contiguous()
+            else:
+                if self._resets_since_refill >= self._K:
+                    self._upload_spawn_table(self._sampler.advance(self._spawn_cursor.cpu().numpy()))
+                cur = self._spawn_cursor.long().clamp_(max=self._K - 1)
+                nodes = torch.gather(self._spawn_table, 1, cur[:, None])[:, 0].contiguous()
+                self._spawn_cursor += mask_u8.to(torch.int32)
+                self._resets_since_refill += 1
+            self._spawn_nodes = nodes
+            outs = self._outs if not self.no_observation else self._outs_noobs
+            _lib.check(self._L.tc_reset(self._h, _ptr(mask_u8), _ptr(nodes), C.byref(outs), self._stream()), "tc_reset")
+        return self.obs, self._info()
+
+    def step(self, action: Dict[str, torch.Tensor]):
+        """env.py:115-147 for all envs. action["car_control"]: float [N,2] (velocity cmd, steering cmd), action["maneuver"]:
+        int [N]. Returns (obs, reward f32[N], terminated bool[N], truncated bool[N], info dict of tensors)."""
+        cc = action["car_control"]
+        man = action["maneuver"]
+        if cc.dtype != torch.float32 or not cc.is_contiguous():
+            cc = cc.to(torch.float32).contiguous()
+        if man.dtype != torch.int32 or not man.is_contiguous():
+            man = man.to(torch.int32).contiguous()
+        if cc.device != self.device or man.device != self.device or cc.shape != (self.num_envs, 2) or man.shape != (self.num_envs,):
+            raise ValueError("action tensors must live on the env's device with shapes [N,2] and [N]")
+        outs = self._outs if not self.no_observation else self._outs_noobs
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tc_step(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
+        o = self.out
+        return self.obs, o["reward"], o["terminated"].view(torch.bool), o["truncated"].view(torch.bool), self._info()
+
+    def reset_done(self):
+        """Auto-reset: resets the envs whose last step terminated or truncated (on the device, no host sync)."""
+        done = self.out["terminated"] | self.out["truncated"]
+        return self.reset(mask=done)
+
+    def step_host(self, car_control: torch.Tensor, maneuver: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor,
+                  truncated: torch.Tensor, cte: Optional[torch.Tensor] = None, heading_error: Optional[torch.Tensor] = None):
+        """The same step with HOST tensors (ideally pinned): actions are copied to the device, the scalar results copied
+        back, and the stream synchronised inside the call (tc_step_host). Observations stay on the device in self.obs."""
+        outs = self._outs if not self.no_observation else self._outs_noobs
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tc_step_host(self._h, _ptr(car_control), _ptr(maneuver), C.byref(outs), _ptr(reward), _ptr(terminated),
+                                            _ptr(truncated), _ptr(cte), _ptr(heading_error), self._stream()), "tc_step_host")
+
+    def render_rgb(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """RGB camera frames [N,H,W,3] at the current poses (renderer.py:36-44), independent of the obs format."""
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((self.num_envs, self.H, self.W, 3), dtype=torch.uint8, device=self.device)
+            _lib.check(self._L.tc_render(self._h, None, _ptr(out), _lib.TC_OBS_RGB, None, None, self._stream()), "tc_render")
+        return out
+
+    def render_obs(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Re-render self.obs at the current poses (after load_state_dict / set_camera_params)."""
+        with torch.cuda.device(self.device):
+            m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            _lib.check(self._L.tc_render(self._h, _ptr(m), _ptr(self.obs), self._fmt, _ptr(self.out.get("seg_count")),
+                                         _ptr(self.out.get("seg_i32")), self._stream()), "tc_render")
+        return self.obs
+
+    # ------------------------------------------------------------------------------------------------ state
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Car state: sf f64 [N,8] (x, y, rot, steering deg, velocity, front x, front y, pad), si i32 [N,16] (path_len,
+        last_maneuver, 4 node pairs, 4 edge ids)."""
+        with torch.cuda.device(self.device):
+            sf = torch.empty((self.num_envs, _lib.TC_SF_N), dtype=torch.float64, device=self.device)
+            si = torch.empty((self.num_envs, _lib.TC_SI_N), dtype=torch.int32, device=self.device)
+            _lib.check(self._L.tc_get_state(self._h, _ptr(sf), _ptr(si), self._stream()), "tc_get_state")
+        return {"sf": sf, "si": si}
+
+    def load_state_dict(self, state: Dict[str, torch.Tensor]):
+        with torch.cuda.device(self.device):
+            sf = state["sf"].to(device=self.device, dtype=torch.float64).contiguous()
+            si = state["si"].to(device=self.device, dtype=torch.int32).contiguous()
+            _lib.check(self._L.tc_set_state(self._h, _ptr(sf), _ptr(si), self._stream()), "tc_set_state")
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def profile_begin(self, max_steps: int):
+        _lib.check(self._L.tc_profile_begin(self._h, int(max_steps)), "tc_profile_begin")
+
+    def profile_end(self):
+        """-> ({"track": ms, "project": ms, "raster": ms} summed over the recorded steps, number of steps)"""
+        ms = (C.c_double * 3)()
+        n = C.c_int32()
+        _lib.check(self._L.tc_profile_end(self._h, ms, C.byref(n)), "tc_profile_end")
+        return {"track": ms[0], "project": ms[1], "raster": ms[2]}, int(n.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.tc_launch_count(self._h))
+
+    def debug_layer_query(self, op: int, pos=(0.0, 0.0), angle: float = 0.0, edge=(0, 0)):
+        """Test hook: a layer.py query evaluated by the device functions on class 0 (tc_debug_layer_query)."""
+        with torch.cuda.device(self.device):
+            oi = torch.zeros(1, dtype=torch.int32, device=self.device)
+            od = torch.zeros(1, dtype=torch.float64, device=self.device)
+            _lib.check(self._L.tc_debug_layer_query(self._h, op, float(pos[0]), float(pos[1]), float(angle), int(edge[0]), int(edge[1]),
+                                                    _ptr(oi), _ptr(od), self._stream()), "tc_debug_layer_query")
+            return int(oi.item()), float(od.item())
