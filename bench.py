@@ -159,7 +159,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     N = args.envs_per_gpu
     cfg = bench_config()
-    env = TinyCarloVecEnv(cfg, N, device=dev, env_index_offset=rank * N)
+    env = TinyCarloVecEnv(cfg, N, device=dev, env_index_offset=rank * N, autoreset="next_step")
     max_steer = float(cfg["car"]["max_steering_angle"])
     speed, k_gain = 0.8, 4.0
     maneuver = torch.zeros(N, dtype=torch.int32, device=dev)
@@ -179,7 +179,6 @@ def main():
         stats[1] += trunc.sum()
         stats[2] += reward.sum()
         stats[3] += N
-        env.reset_done()
 
     def barrier():
         if world > 1:
@@ -228,7 +227,6 @@ def main():
         def step_host():
             cc_np[:, 1] = (head_np + np.arctan2(k_gain * cte_np, speed)) * (180.0 / np.pi / max_steer)
             env.step_host(h_cc, h_man, h_rew, h_term, h_trunc, h_cte, h_head)
-            env.reset_done()
         for _ in range(2):
             step_host()
         barrier()
@@ -259,7 +257,7 @@ def main():
     raster_ms = kern_ms["raster"] / max(kern_steps, 1)
     achieved = N * OBS_BYTES / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "tc_raster_classes_kernel", "kernel_ms_per_launch": raster_ms,
+                "kernel": "tc_render_classes_kernel", "kernel_ms_per_launch": raster_ms,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "step_share": {k: v / max(kern_steps, 1) for k, v in kern_ms.items()}}
 

@@ -111,6 +111,14 @@ TC_API int tc_set_car_params(TcHandle *h, const double *dev_params /*[N,TC_CP_N]
 TC_API int tc_set_camera_params(TcHandle *h, const double *dev_cam /*[N,TC_CAM_N]*/, const int32_t *dev_thickness /*[N]*/, void *stream);
 TC_API int tc_set_wrapped(TcHandle *h, int32_t wrapped); /* 1: reward 0 / terminated false (env.py:137-138) */
 
+/* Next-step autoreset (gymnasium AutoresetMode.NEXT_STEP) inside tc_step: an env whose flag dev_done[i] is set is reset
+ * by the step instead of being advanced (its action is ignored; reward 0, not terminated, not truncated, empty info, obs
+ * of the spawn pose), taking lanepath node dev_spawn_table[i][dev_cursor[i]] and incrementing the cursor; every step
+ * then rewrites dev_done[i] = terminated | truncated. All three buffers are caller-owned device memory that must stay
+ * alive; the caller may OR further termination conditions (wrappers) into dev_done between steps. NULL dev_done = off. */
+TC_API int tc_set_autoreset(TcHandle *h, uint8_t *dev_done /*[N]*/, const int32_t *dev_spawn_table /*[N,table_len]*/, int32_t table_len,
+                            int32_t *dev_cursor /*[N]*/);
+
 /* Reset the envs with dev_mask[i] != 0 (NULL = all) to lanepath node dev_spawn_nodes[i]; renders into obs if non-NULL
  * and zeroes their info outputs like the reference's reset (car.py:47-51). */
 TC_API int tc_reset(TcHandle *h, const uint8_t *dev_mask, const int32_t *dev_spawn_nodes, const TcOutputs *outs, void *stream);
@@ -134,6 +142,10 @@ TC_API int64_t tc_launch_count(const TcHandle *h);
  * tracking, camera-pass and rasterise+store kernels and the number of steps recorded. */
 TC_API int tc_profile_begin(TcHandle *h, int32_t max_steps);
 TC_API int tc_profile_end(TcHandle *h, double *host_ms_sum /*[3]*/, int32_t *host_steps);
+
+/* Debug hook: per-block timeline of the fused render kernel, int64 [N*C][10] = smid, clock64 at block start, tables in
+ * shared memory, camera pass done, rasterisation done, stores issued, segment count, cycles zeroing / set-up / drawing. NULL switches it off. (tools/timeline.py) */
+TC_API int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline);
 
 /* Test hook: the reference's Layer queries (layer.py) evaluated by the DEVICE functions on class 0 of the handle's map.
  * op: 0 get_nearest_edge(pos) 1 get_nearest_edge_with_orientation(pos, a) 2 is_position_within_edge_bounds(pos, e=(i0,i1))

@@ -185,9 +185,9 @@ class OracleVecEnv:
         self.map, self.n, self.H, self.W = omap, n, int(H), int(W)
         self.fmt = 0 if fmt == "classes" else 1
         self.wrapped = bool(wrapped)
-        self.car = np.array(np.broadcast_to(np.asarray(car_params, np.float64).reshape(-1, CP_N), (n, CP_N)))
-        self.cam = np.array(np.broadcast_to(np.asarray(cam_params, np.float64).reshape(-1, CAM_N), (n, CAM_N)))
-        self.thick = np.array(np.broadcast_to(np.asarray(thickness, np.int32).reshape(-1), (n,)))
+        self.car = np.array(np.broadcast_to(np.asarray(car_params, np.float64).reshape(-1, CP_N), (n, CP_N)), order="C")
+        self.cam = np.array(np.broadcast_to(np.asarray(cam_params, np.float64).reshape(-1, CAM_N), (n, CAM_N)), order="C")
+        self.thick = np.array(np.broadcast_to(np.asarray(thickness, np.int32).reshape(-1), (n,)), order="C")
         C = omap.C
         self.sf = np.zeros((n, SF_N), np.float64)
         self.si = np.full((n, SI_N), -1, np.int32)

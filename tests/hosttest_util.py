@@ -60,9 +60,9 @@ class HostCore:
         self.fmt = 0 if fmt == "classes" else 1
         self.wrapped = int(wrapped)
         self.rows_per_band = rows_per_band
-        self.car = np.array(np.broadcast_to(np.asarray(car_rows, np.float64).reshape(-1, 8), (n, 8)))
-        self.cam = np.array(np.broadcast_to(np.asarray(cam_rows, np.float64).reshape(-1, 20), (n, 20)))
-        self.thick = np.array(np.broadcast_to(np.asarray(thickness, np.int32).reshape(-1), (n,)))
+        self.car = np.array(np.broadcast_to(np.asarray(car_rows, np.float64).reshape(-1, 8), (n, 8)), order="C")
+        self.cam = np.array(np.broadcast_to(np.asarray(cam_rows, np.float64).reshape(-1, 20), (n, 20)), order="C")
+        self.thick = np.array(np.broadcast_to(np.asarray(thickness, np.int32).reshape(-1), (n,)), order="C")
         self.sf = np.zeros((n, 8))
         self.si = np.full((n, 16), -1, np.int32)
         self.pose = np.zeros((n, 12))

@@ -65,7 +65,8 @@ def test_host_core_replays_reference_trace(name):
             assert hashlib.sha256(env.obs[0].tobytes()).hexdigest().encode() == g["rgb_sha"][f], (name, f)
 
 
-@pytest.mark.parametrize("H,W,spread,n,nlanes", [(24, 32, 12, 4000, 1), (24, 32, 12, 3000, 32), (48, 64, 300, 2500, 32),
+@pytest.mark.parametrize("H,W,spread,n,nlanes", [(24, 32, 12, 4000, 1), (24, 32, 12, 3000, 32), (24, 32, 12, 3000, -1), (48, 64, 300, 2500, -1),
+                                                  (480, 640, 200, 120, -1), (48, 64, 300, 2500, 32),
                                                   (84, 84, 40, 1500, 32), (480, 640, 200, 120, 32)])
 def test_bitplane_rasteriser_vs_cv2(H, W, spread, n, nlanes):
     rng = np.random.default_rng(H * 7 + W + nlanes)

@@ -34,6 +34,9 @@ struct TcHandle {
     std::vector<void *> allocs;
     unsigned char *d_blob = nullptr;
     TcClassTables *d_classes = nullptr;
+    TcClassBlob *d_cblob_desc = nullptr;
+    unsigned char *d_cblob = nullptr;
+    int max_cblob_bytes = 0;
     int32_t *d_edge_off = nullptr;
     double *d_sf = nullptr;
     int32_t *d_si = nullptr;
@@ -48,7 +51,15 @@ struct TcHandle {
     // raster launch geometry
     int rows_per_band_cls = 0, n_bands_cls = 0, plane_words_cls = 0;
     int rows_per_band_rgb = 0, n_bands_rgb = 0, plane_words_rgb = 0;
-    size_t track_smem = 0, proj_smem = 0;
+    size_t track_smem = 0, proj_smem = 0, render_smem = 0;
+    int max_edges = 0, plane_words_full = 0;
+    int stagger_ns = 0, n_sms = 148;
+    long long *timeline = nullptr;
+    bool fused_ok = false;
+    uint8_t *ar_done = nullptr; // autoreset: caller-owned device buffers
+    const int32_t *ar_table = nullptr;
+    int32_t *ar_cursor = nullptr;
+    int ar_k = 0;
     // optional per-kernel CUDA-event timing (tc_profile_begin/end)
     bool profiling = false;
     int prof_cap = 0, prof_used = 0; // step slots
@@ -156,6 +167,11 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     tc_class_views(map, pk, h->d_blob, d_adj, cls);
     TC_TRYH(tc_dev_alloc(h, &h->d_classes, (size_t)C));
     TC_CUDAH(cudaMemcpy(h->d_classes, cls.data(), sizeof(TcClassTables) * C, cudaMemcpyHostToDevice));
+    TC_TRYH(tc_dev_alloc(h, &h->d_cblob, pk.cblob.size()));
+    TC_CUDAH(cudaMemcpy(h->d_cblob, pk.cblob.data(), pk.cblob.size(), cudaMemcpyHostToDevice));
+    TC_TRYH(tc_dev_alloc(h, &h->d_cblob_desc, (size_t)C));
+    TC_CUDAH(cudaMemcpy(h->d_cblob_desc, pk.cblob_desc.data(), sizeof(TcClassBlob) * C, cudaMemcpyHostToDevice));
+    h->max_cblob_bytes = pk.max_cblob_bytes;
     TC_TRYH(tc_dev_alloc(h, &h->d_edge_off, (size_t)C + 1));
     TC_CUDAH(cudaMemcpy(h->d_edge_off, map->ll_edge_off, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice));
 
@@ -186,6 +202,24 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     const size_t plane_budget = 48 * 1024;
     tc_band_geometry(h->H, h->W, 1, plane_budget, &h->rows_per_band_cls, &h->n_bands_cls, &h->plane_words_cls);
     tc_band_geometry(h->H, h->W, C + 1, 2 * plane_budget, &h->rows_per_band_rgb, &h->n_bands_rgb, &h->plane_words_rgb);
+    for (int c = 0; c < C; c++) h->max_edges = std::max(h->max_edges, map->ll_edge_off[c + 1] - map->ll_edge_off[c]);
+    {
+        cudaDeviceProp prop;
+        TC_CUDAH(cudaGetDeviceProperties(&prop, device));
+        h->n_sms = prop.multiProcessorCount;
+        const char *sg = getenv("TC_STAGGER_NS"); // tuning knob for the first-wave stagger of the fused render kernel
+        if (sg) h->stagger_ns = atoi(sg);
+    }
+    h->plane_words_full = (int)(((size_t)h->H * h->W + 31) / 32) + 1;
+    h->render_smem = tc_render_smem_bytes(h->max_nodes, h->max_edges, h->max_cblob_bytes, h->plane_words_full);
+    h->fused_ok = h->render_smem <= 56 * 1024; // >= 4 blocks per SM; larger frames take the banded two-kernel path
+    if (h->fused_ok) {
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TC_CUDAH(cudaFuncSetAttribute(tc_raster_rgb_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->track_smem));
     TC_CUDAH(cudaFuncSetAttribute(tc_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->proj_smem));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->plane_words_cls * 4)));
@@ -212,6 +246,13 @@ int tc_set_camera_params(TcHandle *h, const double *dev_cam, const int32_t *dev_
     return TC_OK;
 }
 
+int tc_set_autoreset(TcHandle *h, uint8_t *dev_done, const int32_t *dev_spawn_table, int32_t table_len, int32_t *dev_cursor) {
+    if (!h) return tc_fail(TC_ERR_INVALID, "tc_set_autoreset: null handle");
+    if (dev_done && (!dev_spawn_table || !dev_cursor || table_len <= 0)) return tc_fail(TC_ERR_INVALID, "tc_set_autoreset: incomplete spawn table");
+    h->ar_done = dev_done; h->ar_table = dev_spawn_table; h->ar_cursor = dev_cursor; h->ar_k = dev_done ? table_len : 0;
+    return TC_OK;
+}
+
 int tc_set_wrapped(TcHandle *h, int32_t wrapped) {
     if (!h) return tc_fail(TC_ERR_INVALID, "tc_set_wrapped: null handle");
     h->wrapped = wrapped ? 1 : 0;
@@ -221,6 +262,19 @@ int tc_set_wrapped(TcHandle *h, int32_t wrapped) {
 static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int obs_format, int32_t *seg_count_out, int32_t *seg_out,
                             cudaStream_t st, cudaEvent_t after_project = nullptr) {
     const int N = h->n_envs, C = h->C;
+    if (obs && obs_format == TC_OBS_CLASSES && h->fused_ok && !seg_count_out && !seg_out) {
+        TcRenderArgs fa;
+        fa.cblob_desc = h->d_cblob_desc; fa.cblob = h->d_cblob; fa.max_cblob_bytes = h->max_cblob_bytes; fa.n_envs = N; fa.n_classes = C; fa.max_nodes = h->max_nodes; fa.max_edges = h->max_edges;
+        fa.H = h->H; fa.W = h->W; fa.plane_words = h->plane_words_full; fa.pose = h->d_pose; fa.cam = h->d_cam; fa.thickness = h->d_thick;
+        fa.mask = mask; fa.obs = obs;
+        fa.stagger_ns = mask ? 0 : h->stagger_ns; fa.n_sms = h->n_sms;
+        fa.timeline = mask ? nullptr : h->timeline;
+        if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
+        tc_render_classes_kernel<<<N * C, TC_RASTER_THREADS, h->render_smem, st>>>(fa);
+        h->launches++;
+        TC_CUDA(cudaGetLastError());
+        return TC_OK;
+    }
     TcProjArgs pa;
     pa.classes = h->d_classes; pa.n_envs = N; pa.n_classes = C; pa.sum_edges = h->sum_edges; pa.max_nodes = h->max_nodes;
     pa.H = h->H; pa.W = h->W; pa.edge_off = h->d_edge_off; pa.pose = h->d_pose; pa.cam = h->d_cam; pa.mask = mask;
@@ -254,6 +308,7 @@ static int tc_launch_track(TcHandle *h, int mode, const float *cc, const int32_t
     ta.blob = h->d_blob; ta.layout = h->layout; ta.n_envs = h->n_envs; ta.mode = mode; ta.wrapped = h->wrapped;
     ta.sf = h->d_sf; ta.si = h->d_si; ta.car = h->d_car; ta.cam = h->d_cam; ta.pose = h->d_pose;
     ta.act_cc = cc; ta.act_man = man; ta.mask = mask; ta.spawn_nodes = spawn;
+    ta.done = h->ar_done; ta.spawn_table = h->ar_table; ta.spawn_cursor = h->ar_cursor; ta.spawn_k = h->ar_k;
     if (outs) ta.out = *outs;
     const int envs_per_block = TC_TRACK_THREADS / 32;
     tc_track_kernel<<<(h->n_envs + envs_per_block - 1) / envs_per_block, TC_TRACK_THREADS, h->track_smem, st>>>(ta);
@@ -352,6 +407,12 @@ int tc_step_host(TcHandle *h, const float *host_car_control, const int32_t *host
     if (host_cte) TC_CUDA(cudaMemcpyAsync(host_cte, o.cte, N * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (host_heading_error) TC_CUDA(cudaMemcpyAsync(host_heading_error, o.heading_error, N * sizeof(float), cudaMemcpyDeviceToHost, st));
     TC_CUDA(cudaStreamSynchronize(st));
+    return TC_OK;
+}
+
+int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline) {
+    if (!h) return tc_fail(TC_ERR_INVALID, "tc_debug_set_timeline: null handle");
+    h->timeline = dev_timeline;
     return TC_OK;
 }
 

@@ -404,6 +404,26 @@ struct TcClassTables {
     const int32_t *in_edge;
 };
 
+// A class's tables packed back to back for one TMA bulk copy into shared memory (sections 16-byte aligned):
+// [nodes n*16][edges m*8][out_off (n+1)*4][out_edge m*4][in_off (n+1)*4][in_edge m*4]
+struct TcClassBlob {
+    int32_t n_nodes, n_edges;
+    int32_t offset; // byte offset of this class inside the class-blob buffer
+    int32_t bytes;  // multiple of 16
+    int32_t off_edges, off_out_off, off_out_edge, off_in_off, off_in_edge; // relative to `offset`
+};
+TC_HD TcClassTables tc_class_tables_from_blob(const unsigned char *base, const TcClassBlob &b) {
+    TcClassTables ct;
+    ct.n_nodes = b.n_nodes; ct.n_edges = b.n_edges;
+    ct.nodes = (const double *)base;
+    ct.edges = (const int32_t *)(base + b.off_edges);
+    ct.out_off = (const int32_t *)(base + b.off_out_off);
+    ct.out_edge = (const int32_t *)(base + b.off_out_edge);
+    ct.in_off = (const int32_t *)(base + b.off_in_off);
+    ct.in_edge = (const int32_t *)(base + b.off_in_edge);
+    return ct;
+}
+
 // Scratch of one camera pass (shared memory on the device).
 struct TcProjScratch {
     double *Px, *Py, *Pz; // [n]
@@ -510,60 +530,75 @@ TC_HD bool tc_clip_line(int64_t w, int64_t h, int64_t &x1, int64_t &y1, int64_t 
     return (c1 | c2) == 0;
 }
 
+// Truncating integer division for |num| < 2^53 and 0 < |den| < 2^53 through one fp64 division: the correctly rounded
+// quotient is off by at most |q|*2^-53 < 1/|den| <= the distance of a non-integer num/den to the next integer, so the
+// truncation equals C's num / den. (64-bit integer division is ~4x more instructions on the GPU.)
+TC_HD int64_t tc_div_trunc(int64_t num, int64_t den) { return (int64_t)((double)num / (double)den); }
+
+// ---- primitives ----
+// A polyline is first turned into a short list of drawing primitives by scalar code (tc_polyline_setup: the pre-clip,
+// the quad, the clipped outline edges, the scan-line walker events; int64/double, a few hundred instructions, one
+// thread per segment), then the primitives are drawn by lane-parallel loops (tc_prim_draw) whose per-pixel arithmetic
+// is 32-bit. Everything after the pre-clip lies within [-t, W+t] x [-t, H+t] px, i.e. below 2^27 in 16.16.
+enum { TC_PRIM_NONE = 0, TC_PRIM_LINE2 = 1, TC_PRIM_SPAN = 2, TC_PRIM_CIRCLE = 3, TC_PRIM_BRES = 4 };
+#define TC_MAX_PRIMS_PER_SEG 12 // 4 outline edges + <= 6 fill spans + 2 caps
+struct TcPrim {
+    int32_t kind;
+    int32_t a[7];
+};
+
 // thickness <= 1: LineIterator (8-connected, left to right). Step i of the Bresenham walk sits at major offset i and
 // minor offset c_i = floor((2*dy*i + dx - 1) / (2*dx)) — the closed form of `err` staying in [-2dy, 2dx-2dy).
-TC_HD void tc_line_bresenham(const TcLanes &g, const TcPlane &pl, int64_t x1, int64_t y1, int64_t x2, int64_t y2) {
-    if (x1 < 0 || x1 >= pl.W || x2 < 0 || x2 >= pl.W || y1 < 0 || y1 >= pl.H || y2 < 0 || y2 >= pl.H)
-        if (!tc_clip_line(pl.W, pl.H, x1, y1, x2, y2)) return;
+TC_HD int tc_setup_bresenham(int W, int H, int64_t x1, int64_t y1, int64_t x2, int64_t y2, TcPrim *out) {
+    if (x1 < 0 || x1 >= W || x2 < 0 || x2 >= W || y1 < 0 || y1 >= H || y2 < 0 || y2 >= H)
+        if (!tc_clip_line(W, H, x1, y1, x2, y2)) return 0;
     int64_t dx = x2 - x1, dy = y2 - y1;
     int sy = 1;
     if (dx < 0) { dx = -dx; dy = -dy; x1 = x2; y1 = y2; }
     if (dy < 0) { dy = -dy; sy = -1; }
-    bool vert = dy > dx;
+    int vert = dy > dx;
     if (vert) { int64_t t = dx; dx = dy; dy = t; }
-    if (dx == 0) {
-        if (g.lane == 0) tc_put(pl, x1, y1);
-        return;
-    }
-    for (int64_t i = g.lane; i <= dx; i += g.n) {
-        int64_t c = (2 * dy * i + dx - 1) / (2 * dx);
-        if (vert) tc_put(pl, x1 + c, y1 + sy * i);
-        else tc_put(pl, x1 + i, y1 + sy * c);
-    }
+    out->kind = TC_PRIM_BRES;
+    out->a[0] = vert; out->a[1] = (int32_t)x1; out->a[2] = (int32_t)y1; out->a[3] = sy; out->a[4] = (int32_t)dx; out->a[5] = (int32_t)dy;
+    out->a[6] = 0;
+    return 1;
 }
 
-// 16.16 DDA of the quad outline
-TC_HD void tc_line2(const TcLanes &g, const TcPlane &pl, int64_t x1, int64_t y1, int64_t x2, int64_t y2) {
-    if (!tc_clip_line((int64_t)pl.W << TC_XY_SHIFT, (int64_t)pl.H << TC_XY_SHIFT, x1, y1, x2, y2)) return;
-    int64_t dx = x2 - x1, dy = y2 - y1, ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, xs, ys, n;
-    bool xmajor = ax > ay;
+// 16.16 DDA of one quad outline edge
+TC_HD int tc_setup_line2(int W, int H, int64_t x1, int64_t y1, int64_t x2, int64_t y2, TcPrim *out) {
+    if (!tc_clip_line((int64_t)W << TC_XY_SHIFT, (int64_t)H << TC_XY_SHIFT, x1, y1, x2, y2)) return 0;
+    int64_t dx = x2 - x1, dy = y2 - y1, ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, step, n;
+    int xmajor = ax > ay;
     if (xmajor) {
         if (dx < 0) { dy = -dy; int64_t t; t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
-        xs = TC_XY_ONE;
-        ys = (dy * TC_XY_ONE) / (ax | 1);
+        step = tc_div_trunc(dy * TC_XY_ONE, ax | 1);
         n = (x2 - x1) >> TC_XY_SHIFT;
     } else {
         if (dy < 0) { dx = -dx; int64_t t; t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
-        xs = (dx * TC_XY_ONE) / (ay | 1);
-        ys = TC_XY_ONE;
+        step = tc_div_trunc(dx * TC_XY_ONE, ay | 1);
         n = (y2 - y1) >> TC_XY_SHIFT;
     }
     x1 += TC_XY_ONE >> 1;
     y1 += TC_XY_ONE >> 1;
-    if (g.lane == 0) tc_put(pl, (x2 + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT, (y2 + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT);
-    if (xmajor) {
-        int64_t x0 = x1 >> TC_XY_SHIFT;
-        for (int64_t i = g.lane; i <= n; i += g.n) tc_put(pl, x0 + i, (y1 + i * ys) >> TC_XY_SHIFT);
-    } else {
-        int64_t y0 = y1 >> TC_XY_SHIFT;
-        for (int64_t i = g.lane; i <= n; i += g.n) tc_put(pl, (x1 + i * xs) >> TC_XY_SHIFT, y0 + i);
-    }
+    out->kind = TC_PRIM_LINE2;
+    out->a[0] = xmajor;
+    out->a[1] = (int32_t)(xmajor ? (x1 >> TC_XY_SHIFT) : (y1 >> TC_XY_SHIFT)); // integer start on the major axis
+    out->a[2] = (int32_t)(xmajor ? y1 : x1);                                    // 16.16 start on the minor axis
+    out->a[3] = (int32_t)step;
+    out->a[4] = (int32_t)n;
+    out->a[5] = (int32_t)((x2 + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT); // the extra end-point pixel
+    out->a[6] = (int32_t)((y2 + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT);
+    return 1;
 }
 
 // FillConvexPoly (4 vertices, shift 16). The scan-line loop only changes walker state on rows where a walker reaches
-// the end of its polygon edge; between such rows x advances linearly, so every lane replays the (<= 5) events and the
-// rows of each span are spread over the lanes.
-TC_HD void tc_fill_convex_poly4(const TcLanes &g, const TcPlane &pl, const int64_t (*v)[2]) {
+// the end of its polygon edge; between such rows x advances linearly. The (<= 6) events are replayed here and every
+// run of rows becomes one SPAN primitive; the outline edges become LINE2 primitives.
+// Fixed slots of a segment's primitive list: 0-3 outline edges, 4-9 fill spans, 10-11 caps (or slot 0: Bresenham line).
+enum { TC_SLOT_EDGE0 = 0, TC_SLOT_SPAN0 = 4, TC_SLOT_CAP0 = 10 };
+enum { TC_ROLE_SPANS = 0, TC_ROLE_EDGE0 = 1 /* ..4 */, TC_ROLE_CAPS = 5, TC_N_ROLES = 6, TC_ROLE_ALL = -1 };
+
+TC_HD void tc_setup_fill_convex_poly4(int W, int H, const int64_t (*v)[2], int role, TcPrim *out) {
     const int npts = 4;
     const int64_t delta = TC_XY_ONE >> 1;
     int imin = 0, edges = npts;
@@ -574,13 +609,15 @@ TC_HD void tc_fill_convex_poly4(const TcLanes &g, const TcPlane &pl, const int64
         if (v[i][1] > ymax) ymax = v[i][1];
         if (v[i][0] > xmax) xmax = v[i][0];
         if (v[i][0] < xmin) xmin = v[i][0];
-        tc_line2(g, pl, p0x, p0y, v[i][0], v[i][1]);
+        if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + i) tc_setup_line2(W, H, p0x, p0y, v[i][0], v[i][1], out + TC_SLOT_EDGE0 + i);
         p0x = v[i][0]; p0y = v[i][1];
     }
+    if (role != TC_ROLE_ALL && role != TC_ROLE_SPANS) return;
+    int k = TC_SLOT_SPAN0;
     xmin = (xmin + delta) >> TC_XY_SHIFT; xmax = (xmax + delta) >> TC_XY_SHIFT;
     ymin = (ymin + delta) >> TC_XY_SHIFT; ymax = (ymax + delta) >> TC_XY_SHIFT;
-    if ((int)xmax < 0 || (int)ymax < 0 || (int)xmin >= pl.W || (int)ymin >= pl.H) return;
-    if (ymax > pl.H - 1) ymax = pl.H - 1;
+    if ((int)xmax < 0 || (int)ymax < 0 || (int)xmin >= W || (int)ymin >= H) return;
+    if (ymax > H - 1) ymax = H - 1;
     int y = (int)ymin;
     int e_idx[2] = {imin, imin}, e_di[2] = {1, npts - 1}, e_ye[2] = {y, y};
     int64_t e_x[2] = {-TC_XY_ONE, -TC_XY_ONE}, e_dx[2] = {0, 0};
@@ -595,7 +632,7 @@ TC_HD void tc_fill_convex_poly4(const TcLanes &g, const TcPlane &pl, const int64
                     if (ty > y) {
                         int64_t xs = v[idx0][0], xe = v[idx][0];
                         e_ye[i] = ty;
-                        e_dx[i] = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+                        e_dx[i] = tc_div_trunc((xe - xs) * 2 + (ty - y), 2 * (ty - y));
                         e_x[i] = xs;
                         e_idx[i] = idx;
                         break;
@@ -607,22 +644,16 @@ TC_HD void tc_fill_convex_poly4(const TcLanes &g, const TcPlane &pl, const int64
             }
         }
         if (edges < 0) break;
-        // rows y .. y_end-1 share the walker state: next event is the smaller ye (both are > y here), capped by ymax
+        // rows y .. y_end-1 share the walker state: the next event is the smaller ye (both are > y here), capped by ymax
         int y_end = e_ye[0] < e_ye[1] ? e_ye[0] : e_ye[1];
         if (y_end > (int)ymax + 1) y_end = (int)ymax + 1;
-        if (y_end <= y) y_end = y + 1; // a walker that found no edge keeps its stale ye; advance row by row like the reference
+        if (y_end <= y) y_end = y + 1;
         int r0 = y < 0 ? 0 : y;
-        if (r0 < pl.y_lo) r0 = pl.y_lo;
-        int r1 = y_end < pl.y_hi ? y_end : pl.y_hi;
-        for (int r = r0 + g.lane; r < r1; r += g.n) {
-            int64_t xa = e_x[0] + (int64_t)(r - y) * e_dx[0], xb = e_x[1] + (int64_t)(r - y) * e_dx[1];
-            int64_t xl = xa > xb ? xb : xa, xr = xa > xb ? xa : xb;
-            int xx1 = (int)((xl + delta) >> TC_XY_SHIFT), xx2 = (int)((xr + delta) >> TC_XY_SHIFT);
-            if (xx2 >= 0 && xx1 < pl.W) {
-                if (xx1 < 0) xx1 = 0;
-                if (xx2 >= pl.W) xx2 = pl.W - 1;
-                tc_hline(pl, r, xx1, xx2);
-            }
+        if (r0 < y_end && k < TC_SLOT_CAP0) {
+            TcPrim &q = out[k++];
+            q.kind = TC_PRIM_SPAN;
+            q.a[0] = y; q.a[1] = r0; q.a[2] = y_end;
+            q.a[3] = (int32_t)e_x[0]; q.a[4] = (int32_t)e_dx[0]; q.a[5] = (int32_t)e_x[1]; q.a[6] = (int32_t)e_dx[1];
         }
         e_x[0] += (int64_t)(y_end - y) * e_dx[0];
         e_x[1] += (int64_t)(y_end - y) * e_dx[1];
@@ -631,7 +662,56 @@ TC_HD void tc_fill_convex_poly4(const TcLanes &g, const TcPlane &pl, const int64
     }
 }
 
-// filled midpoint circle; the (radius+1)-step outer loop is replayed by every lane, the 4 spans of a step go to lanes 0..3
+TC_HD int64_t tc_cv_round(double v) { return (int64_t)rint(v); } // round half to even
+
+// cv2.polylines(img, np.int32([[p0, p1]]), False, 255, t) -> primitives in the 12 fixed slots of `out` (the caller has
+// set every slot to TC_PRIM_NONE). `role` selects which slots this call fills, so that the independent parts of one
+// segment can be set up by different threads (each repeats the cheap pre-clip and quad construction): TC_ROLE_SPANS,
+// TC_ROLE_EDGE0+i, TC_ROLE_CAPS, or TC_ROLE_ALL.
+TC_HD void tc_polyline_setup(int W, int H, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int t, int role, TcPrim *out) {
+    int64_t ax = x0, ay = y0, bx = x1, by = y1;
+    if (t <= 1) {
+        if (role == TC_ROLE_ALL || role == TC_ROLE_SPANS) tc_setup_bresenham(W, H, ax, ay, bx, by, out);
+        return;
+    }
+    ax += t; ay += t; bx += t; by += t;
+    if (!tc_clip_line((int64_t)W + 2 * t, (int64_t)H + 2 * t, ax, ay, bx, by)) return;
+    ax -= t; ay -= t; bx -= t; by -= t;
+    int64_t P0x = ax << TC_XY_SHIFT, P0y = ay << TC_XY_SHIFT, P1x = bx << TC_XY_SHIFT, P1y = by << TC_XY_SHIFT;
+    int64_t T = (int64_t)t << (TC_XY_SHIFT - 1);
+    if (role != TC_ROLE_CAPS) {
+        const double INV = 1.0 / TC_XY_ONE;
+        double dx = (double)(P0x - P1x) * INV, dy = (double)(P1y - P0y) * INV;
+        double r = dx * dx + dy * dy;
+        int odd = t & 1;
+        if (fabs(r) > 2.220446049250313e-16) {
+            r = ((double)T + odd * TC_XY_ONE * 0.5) / sqrt(r);
+            int64_t dpx = tc_cv_round(dy * r), dpy = tc_cv_round(dx * r);
+            int64_t v[4][2] = {{P0x + dpx, P0y + dpy}, {P0x - dpx, P0y - dpy}, {P1x - dpx, P1y - dpy}, {P1x + dpx, P1y + dpy}};
+            tc_setup_fill_convex_poly4(W, H, v, role, out);
+        }
+    }
+    if (role == TC_ROLE_ALL || role == TC_ROLE_CAPS) {
+        int rad = (int)((T + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT);
+        for (int e = 0; e < 2; e++) {
+            TcPrim &q = out[TC_SLOT_CAP0 + e];
+            q.kind = TC_PRIM_CIRCLE;
+            q.a[0] = (int32_t)(((e ? P1x : P0x) + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT);
+            q.a[1] = (int32_t)(((e ? P1y : P0y) + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT);
+            q.a[2] = rad;
+            q.a[3] = q.a[4] = q.a[5] = q.a[6] = 0;
+        }
+    }
+}
+
+// 32-bit pixel helpers (coordinates are frame-sized here)
+TC_HD void tc_put32(const TcPlane &pl, int x, int y) {
+    if ((unsigned)x >= (unsigned)pl.W || y < pl.y_lo || y >= pl.y_hi) return;
+    int b = (y - pl.y_lo) * pl.W + x;
+    tc_or_word(pl.bits + (b >> 5), 1u << (b & 31));
+}
+
+// filled midpoint circle; the (radius+1)-step outer loop is replayed by every lane, the 4 spans of a step go to 4 lanes
 TC_HD void tc_circle_filled(const TcLanes &g, const TcPlane &pl, int cx, int cy, int radius) {
     int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
     int it = 0;
@@ -662,32 +742,50 @@ TC_HD void tc_circle_filled(const TcLanes &g, const TcPlane &pl, int cx, int cy,
     }
 }
 
-TC_HD int64_t tc_cv_round(double v) { return (int64_t)rint(v); } // round half to even
+// draws one primitive with the lanes of the group
+TC_HD void tc_prim_draw(const TcLanes &g, const TcPlane &pl, const TcPrim &q) {
+    if (q.kind == TC_PRIM_LINE2) {
+        const int base = q.a[1], fix = q.a[2], step = q.a[3], n = q.a[4];
+        if (g.lane == 0) tc_put32(pl, q.a[5], q.a[6]);
+        if (q.a[0]) for (int i = g.lane; i <= n; i += g.n) tc_put32(pl, base + i, (fix + i * step) >> TC_XY_SHIFT);
+        else for (int i = g.lane; i <= n; i += g.n) tc_put32(pl, (fix + i * step) >> TC_XY_SHIFT, base + i);
+    } else if (q.kind == TC_PRIM_SPAN) {
+        const int y = q.a[0];
+        int r0 = q.a[1] > pl.y_lo ? q.a[1] : pl.y_lo;
+        int r1 = q.a[2] < pl.y_hi ? q.a[2] : pl.y_hi;
+        for (int r = r0 + g.lane; r < r1; r += g.n) {
+            int xa = q.a[3] + (r - y) * q.a[4], xb = q.a[5] + (r - y) * q.a[6];
+            int xl = xa > xb ? xb : xa, xr = xa > xb ? xa : xb;
+            int xx1 = (xl + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT, xx2 = (xr + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT;
+            if (xx2 >= 0 && xx1 < pl.W) {
+                if (xx1 < 0) xx1 = 0;
+                if (xx2 >= pl.W) xx2 = pl.W - 1;
+                tc_hline(pl, r, xx1, xx2);
+            }
+        }
+    } else if (q.kind == TC_PRIM_CIRCLE) {
+        tc_circle_filled(g, pl, q.a[0], q.a[1], q.a[2]);
+    } else if (q.kind == TC_PRIM_BRES) {
+        const int vert = q.a[0], x1 = q.a[1], y1 = q.a[2], sy = q.a[3];
+        const unsigned dx = (unsigned)q.a[4], dy = (unsigned)q.a[5];
+        if (dx == 0) {
+            if (g.lane == 0) tc_put32(pl, x1, y1);
+            return;
+        }
+        for (unsigned i = g.lane; i <= dx; i += g.n) {
+            // 2*dy*i + dx - 1 < 2^32 for frame-sized lines (dx, dy < 2^15)
+            int c = (int)((2u * dy * i + dx - 1u) / (2u * dx));
+            if (vert) tc_put32(pl, x1 + c, y1 + sy * (int)i);
+            else tc_put32(pl, x1 + (int)i, y1 + sy * c);
+        }
+    }
+}
 
-// cv2.polylines(img, np.int32([[p0, p1]]), False, 255, t) into the bit plane
+// setup + draw by one group (every lane replays the scalar setup); the fused kernel splits the two phases instead
 TC_HD void tc_polyline2(const TcLanes &g, const TcPlane &pl, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int t) {
-    int64_t ax = x0, ay = y0, bx = x1, by = y1;
-    if (t > 1) {
-        ax += t; ay += t; bx += t; by += t;
-        if (!tc_clip_line((int64_t)pl.W + 2 * t, (int64_t)pl.H + 2 * t, ax, ay, bx, by)) return;
-        ax -= t; ay -= t; bx -= t; by -= t;
-    } else {
-        tc_line_bresenham(g, pl, ax, ay, bx, by);
-        return;
-    }
-    int64_t P0x = ax << TC_XY_SHIFT, P0y = ay << TC_XY_SHIFT, P1x = bx << TC_XY_SHIFT, P1y = by << TC_XY_SHIFT;
-    const double INV = 1.0 / TC_XY_ONE;
-    double dx = (double)(P0x - P1x) * INV, dy = (double)(P1y - P0y) * INV;
-    double r = dx * dx + dy * dy;
-    int odd = t & 1;
-    int64_t T = (int64_t)t << (TC_XY_SHIFT - 1);
-    if (fabs(r) > 2.220446049250313e-16) {
-        r = ((double)T + odd * TC_XY_ONE * 0.5) / sqrt(r);
-        int64_t dpx = tc_cv_round(dy * r), dpy = tc_cv_round(dx * r);
-        int64_t v[4][2] = {{P0x + dpx, P0y + dpy}, {P0x - dpx, P0y - dpy}, {P1x - dpx, P1y - dpy}, {P1x + dpx, P1y + dpy}};
-        tc_fill_convex_poly4(g, pl, v);
-    }
-    int rad = (int)((T + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT);
-    tc_circle_filled(g, pl, (int)((P0x + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT), (int)((P0y + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT), rad);
-    tc_circle_filled(g, pl, (int)((P1x + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT), (int)((P1y + (TC_XY_ONE >> 1)) >> TC_XY_SHIFT), rad);
+    TcPrim prims[TC_MAX_PRIMS_PER_SEG];
+    for (int i = 0; i < TC_MAX_PRIMS_PER_SEG; i++) prims[i].kind = TC_PRIM_NONE;
+    tc_polyline_setup(pl.W, pl.H, x0, y0, x1, y1, t, TC_ROLE_ALL, prims);
+    for (int i = 0; i < TC_MAX_PRIMS_PER_SEG; i++)
+        if (prims[i].kind != TC_PRIM_NONE) tc_prim_draw(g, pl, prims[i]);
 }

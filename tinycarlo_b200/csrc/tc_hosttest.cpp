@@ -145,9 +145,20 @@ HT_API void ht_render(const HtMap *m, int n, int H, int W, int fmt, int rows_per
 HT_API void ht_polyline(uint8_t *img, int H, int W, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int thickness, int y_lo, int y_hi,
                         int nlanes) {
     if (y_hi <= 0) { y_lo = 0; y_hi = H; }
-    if (nlanes <= 0) nlanes = 1;
+    if (nlanes == 0) nlanes = 1;
     std::vector<uint32_t> plane(((size_t)(y_hi - y_lo) * W + 31) / 32 + 1, 0);
     TcPlane pl = {plane.data(), H, W, y_lo, y_hi};
+    if (nlanes < 0) {
+        // the fused kernel's split: every role sets up its own slots (as different warps do), then 32 lanes draw
+        TcPrim prims[TC_MAX_PRIMS_PER_SEG];
+        for (int i = 0; i < TC_MAX_PRIMS_PER_SEG; i++) prims[i].kind = TC_PRIM_NONE;
+        for (int role = 0; role < TC_N_ROLES; role++) tc_polyline_setup(W, H, x0, y0, x1, y1, thickness, role, prims);
+        for (int lane = 0; lane < 32; lane++) {
+            TcLanes g = {lane, 32};
+            for (int i = 0; i < TC_MAX_PRIMS_PER_SEG; i++)
+                if (prims[i].kind != TC_PRIM_NONE) tc_prim_draw(g, pl, prims[i]);
+        }
+    } else
     for (int lane = 0; lane < nlanes; lane++) {
         TcLanes g = {lane, nlanes};
         tc_polyline2(g, pl, x0, y0, x1, y1, thickness);

@@ -63,6 +63,11 @@ struct TcTrackArgs {
     const int32_t *act_man;
     const uint8_t *mask;        // reset: envs to reset (NULL = all)
     const int32_t *spawn_nodes; // reset
+    // next-step autoreset (gymnasium AutoresetMode.NEXT_STEP): an env whose previous step ended is reset by this step
+    uint8_t *done;              // [N] in/out, NULL = autoreset off
+    const int32_t *spawn_table; // [N, spawn_k] pre-drawn spawn nodes
+    int32_t *spawn_cursor;      // [N]
+    int spawn_k;
     TcOutputs out;
 };
 
@@ -90,7 +95,17 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS) tc_track_kernel(const TcTrac
     int32_t *si = a.si + (size_t)env * TC_SI_N;
     TcCarState s;
     bool truncated = false;
-    if (a.mode == 1) {
+    bool auto_reset = false;
+    if (a.mode == 0 && a.done && a.done[env]) {
+        // the action of this step is ignored; reward 0, not terminated, not truncated, empty info (env.py:101-113)
+        int cur = a.spawn_cursor[env];
+        int node = a.spawn_table[(size_t)env * a.spawn_k + (cur < a.spawn_k ? cur : a.spawn_k - 1)];
+        tc_load_state(sf, si, s);
+        auto_reset = tc_car_reset(t, cp, s, node);
+        if (auto_reset && g.lane == 0) a.spawn_cursor[env] = cur + 1;
+    }
+    if (auto_reset) {
+    } else if (a.mode == 1) {
         if (a.mask && !a.mask[env]) return;
         tc_load_state(sf, si, s);
         if (!tc_car_reset(t, cp, s, a.spawn_nodes[env])) return;
@@ -103,7 +118,9 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS) tc_track_kernel(const TcTrac
     double dist[TC_MAX_CLASSES];
     int nearest[TC_MAX_CLASSES];
     TcInfo info = tc_get_info(g, t, cp, s, a.wrapped != 0, dist, nearest);
+    if (auto_reset) { info.reward = 0; info.terminated = false; }
     if (g.lane != 0) return;
+    if (a.mode == 0 && a.done) a.done[env] = (info.terminated || truncated) ? 1 : 0;
     tc_store_state(sf, si, s);
     // pose for the camera pass: front-axle update already evaluated cos/sin(rot); recomputing keeps the code simple
     tc_camera_pose(a.cam + (size_t)env * TC_CAM_N + TC_CAM_E, s.x, s.y, cos(s.rot), sin(s.rot), a.pose + (size_t)env * 12);
@@ -400,6 +417,170 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const 
         tc_st_cs(o4 + j, v);
     }
     for (size_t i = head + (nvec << 4) + threadIdx.x; i < nbytes; i += TC_RASTER_THREADS) out[i] = byte_at(i);
+}
+
+
+// ------------------------------------------------------------------------------------------------ fused camera pass + rasterise + store
+// classes, single band: a block per (env, class) runs the camera pass in shared memory, keeps the segments on chip,
+// rasterises them into the bit plane and streams the plane out. The latency of the geometry of one block hides behind
+// the stores of the other blocks resident on the SM; no segment list goes through global memory.
+struct TcRenderArgs {
+    const TcClassBlob *cblob_desc; // [C] device
+    const unsigned char *cblob;    // class blobs (global)
+    int n_envs, n_classes, max_nodes, max_edges, max_cblob_bytes;
+    int H, W;
+    int plane_words;           // words of the full-frame bit plane (incl. pad word)
+    const double *pose;        // [N,12]
+    const double *cam;         // [N,TC_CAM_N]
+    const int32_t *thickness;  // [N]
+    const uint8_t *mask;       // optional
+    uint8_t *obs;              // [N,C,H,W]
+    int stagger_ns, n_sms;     // first-wave phase stagger (see the kernel)
+    long long *timeline;       // optional debug [N*C][10]: smid, clock at start / tables landed / geometry done / raster done / end
+};
+
+// shared memory: [union{ camera-pass scratch + the class's tables (TMA) | bit plane }][segment list]
+__host__ __device__ inline size_t tc_render_scratch_bytes(int max_nodes) { return (tc_proj_smem_bytes(max_nodes) + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t tc_render_union_bytes(int max_nodes, int max_cblob_bytes, int plane_words) {
+    size_t a = tc_render_scratch_bytes(max_nodes) + (size_t)max_cblob_bytes, b = (size_t)plane_words * 4;
+    return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
+#define TC_SETUP_CHUNK 16 // segments set up per round (one thread each), then drawn by all warps
+__host__ __device__ inline size_t tc_render_segs_bytes(int max_edges) { return (size_t)(max_edges > 0 ? max_edges : 1) * 16; }
+__host__ __device__ inline size_t tc_render_smem_bytes(int max_nodes, int max_edges, int max_cblob_bytes, int plane_words) {
+    return tc_render_union_bytes(max_nodes, max_cblob_bytes, plane_words) + tc_render_segs_bytes(max_edges) +
+           (size_t)TC_SETUP_CHUNK * TC_MAX_PRIMS_PER_SEG * sizeof(TcPrim);
+}
+
+__global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_render_classes_kernel(const TcRenderArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int seg_cnt;
+    __shared__ __align__(8) uint64_t bar;
+    const int env = blockIdx.x / a.n_classes, c = blockIdx.x % a.n_classes;
+    if (a.mask && !a.mask[env]) return;
+    const int tid = threadIdx.x;
+    // Every block does a latency-bound geometry phase and then a bandwidth-bound store phase. Blocks that share an SM
+    // start together and, sharing the SM's store bandwidth equally, finish together, so their successors start together
+    // again: the SM's HBM share idles during every geometry phase (measured: ~10% of the kernel). Delaying the k-th
+    // resident block of the first wave by k * stagger_ns puts the co-resident blocks out of phase once; the staggered
+    // state then sustains itself (a block in its geometry phase lends its bandwidth share to the others).
+    if (a.stagger_ns > 0 && (int)blockIdx.x < 4 * a.n_sms) {
+        const unsigned slot = blockIdx.x / a.n_sms;
+        if (slot) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(500);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            } while (t1 - t0 < (unsigned long long)slot * a.stagger_ns);
+        }
+    }
+    long long tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0, tl_setup = 0, tl_draw = 0, tl_z = 0;
+    if (a.timeline && tid == 0) tl0 = clock64();
+    const TcClassBlob cb = a.cblob_desc[c];
+    unsigned char *tab_smem = smem_raw + tc_render_scratch_bytes(a.max_nodes);
+    if (tid == 0) {
+        seg_cnt = 0;
+        tc_mbar_init(&bar, 1);
+        tc_fence_mbar_init();
+        tc_mbar_expect_tx(&bar, (uint32_t)cb.bytes);
+        tc_bulk_g2s(tab_smem, a.cblob + cb.offset, (uint32_t)cb.bytes, &bar);
+    }
+    const int n = cb.n_nodes, m = cb.n_edges;
+    int4 *segs = (int4 *)(smem_raw + tc_render_union_bytes(a.max_nodes, a.max_cblob_bytes, a.plane_words));
+    uint32_t *plane = (uint32_t *)smem_raw;
+    {
+        const size_t np = (size_t)((a.max_nodes + 15) & ~15);
+        TcProjScratch sc;
+        sc.Px = (double *)smem_raw; sc.Py = sc.Px + np; sc.Pz = sc.Py + np;
+        sc.ix = (int32_t *)(sc.Pz + np); sc.iy = sc.ix + np;
+        uint8_t *fA = (uint8_t *)(sc.iy + np), *fB = fA + np, *rA = fB + np, *rB = rA + np;
+        sc.vis = rB + np; sc.front = fA; sc.inr = rA;
+        double pose[12], cam[TC_CAM_N];
+#pragma unroll
+        for (int i = 0; i < 12; i++) pose[i] = a.pose[(size_t)env * 12 + i];
+#pragma unroll
+        for (int i = TC_CAM_FX; i <= TC_CAM_MAX_RANGE; i++) cam[i] = a.cam[(size_t)env * TC_CAM_N + i];
+        const double max_range = cam[TC_CAM_MAX_RANGE];
+        __syncthreads();      // barrier init visible to all threads
+        tc_mbar_wait(&bar, 0); // the class's tables have landed in shared memory
+        if (a.timeline && tid == 0) tl1 = clock64();
+        const TcClassTables ct = tc_class_tables_from_blob(tab_smem, cb);
+        for (int v = tid; v < n; v += TC_RASTER_THREADS) {
+            double X, Y, Z;
+            tc_transform_node(pose, ct.nodes[2 * v], ct.nodes[2 * v + 1], X, Y, Z);
+            sc.Px[v] = X; sc.Py[v] = Y; sc.Pz[v] = Z;
+            fA[v] = Z < 0;
+        }
+        __syncthreads();
+        for (int v = tid; v < n; v += TC_RASTER_THREADS) fB[v] = fA[v] | (uint8_t)tc_clip_pass_node(ct, sc, fA, v, true, -0.0000001);
+        __syncthreads();
+        for (int v = tid; v < n; v += TC_RASTER_THREADS) fA[v] = fB[v] | (uint8_t)tc_clip_pass_node(ct, sc, fB, v, false, -0.0000001);
+        __syncthreads();
+        for (int v = tid; v < n; v += TC_RASTER_THREADS) rA[v] = sc.Pz[v] > -max_range;
+        __syncthreads();
+        for (int v = tid; v < n; v += TC_RASTER_THREADS) rB[v] = rA[v] | (uint8_t)tc_clip_pass_node(ct, sc, rA, v, true, -max_range);
+        __syncthreads();
+        for (int v = tid; v < n; v += TC_RASTER_THREADS) rA[v] = rB[v] | (uint8_t)tc_clip_pass_node(ct, sc, rB, v, false, -max_range);
+        __syncthreads();
+        for (int v = tid; v < n; v += TC_RASTER_THREADS) {
+            double u, w;
+            tc_project(cam, sc.Px[v], sc.Py[v], sc.Pz[v], u, w);
+            sc.ix[v] = tc_np_int32(u);
+            sc.iy[v] = tc_np_int32(w);
+            sc.vis[v] = (u > 0 && u < a.W && w > 0 && w < a.H && fA[v] && rA[v]) ? 1 : 0;
+        }
+        __syncthreads();
+        // kept edges (camera.py:95); order is irrelevant for a single-colour plane
+        for (int e = tid; e < m; e += TC_RASTER_THREADS) {
+            int n0 = ct.edges[2 * e], n1 = ct.edges[2 * e + 1];
+            if (sc.vis[n0] || sc.vis[n1]) segs[atomicAdd(&seg_cnt, 1)] = make_int4(sc.ix[n0], sc.iy[n0], sc.ix[n1], sc.iy[n1]);
+        }
+        __syncthreads(); // scratch and tables are dead from here on; the plane takes their place
+    }
+    const int cnt = seg_cnt;
+    if (a.timeline && tid == 0) tl2 = clock64();
+    uint8_t *out = a.obs + ((size_t)env * a.n_classes + c) * a.H * a.W;
+    const size_t nbytes = (size_t)a.H * a.W;
+    if (cnt > 0) {
+        for (int i = tid; i < a.plane_words; i += TC_RASTER_THREADS) plane[i] = 0;
+        __syncthreads();
+        if (a.timeline && tid == 0) tl_z = clock64();
+        const int t = a.thickness[env];
+        TcPlane pl = {plane, a.H, a.W, 0, a.H};
+        const int warp = tid >> 5, lane = tid & 31;
+        TcLanes g = {lane, 32};
+        TcPrim *prims = (TcPrim *)((unsigned char *)segs + tc_render_segs_bytes(a.max_edges));
+        for (int base = 0; base < cnt; base += TC_SETUP_CHUNK) {
+            const int nseg = min(TC_SETUP_CHUNK, cnt - base);
+            long long tc0 = 0;
+            if (a.timeline && tid == 0) tc0 = clock64();
+            // scalar set-up of up to 16 segments: warp r takes role r (fill spans, one outline edge each, caps) of all of
+            // them, lane = segment, so a warp runs one code path
+            for (int i = tid; i < nseg * TC_MAX_PRIMS_PER_SEG; i += TC_RASTER_THREADS) prims[i].kind = TC_PRIM_NONE;
+            __syncthreads();
+            if (warp < TC_N_ROLES && lane < nseg) {
+                int4 s4 = segs[base + lane];
+                tc_polyline_setup(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, warp, prims + lane * TC_MAX_PRIMS_PER_SEG);
+            }
+            __syncthreads();
+            if (a.timeline && tid == 0) { long long x = clock64(); tl_setup += x - tc0; tc0 = x; }
+            // pixels: the primitives go round-robin to the warps, the pixels / rows of a primitive to the lanes
+            for (int p = warp; p < nseg * TC_MAX_PRIMS_PER_SEG; p += TC_RASTER_THREADS / 32)
+                if (prims[p].kind != TC_PRIM_NONE) tc_prim_draw(g, pl, prims[p]);
+            __syncthreads();
+            if (a.timeline && tid == 0) tl_draw += clock64() - tc0;
+        }
+    }
+    if (a.timeline && tid == 0) tl3 = clock64();
+    tc_store_plane(out, nbytes, plane, cnt > 0);
+    if (a.timeline && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *r = a.timeline + (size_t)blockIdx.x * 10;
+        r[0] = smid; r[1] = tl0; r[2] = tl1; r[3] = tl2; r[4] = tl3; r[5] = clock64();
+        r[6] = cnt; r[7] = tl_z ? tl_z - tl2 : 0; r[8] = tl_setup; r[9] = tl_draw;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ test hook

@@ -13,6 +13,9 @@ struct TcPacked {
     std::vector<int32_t> adj;        // per class: [out_off(n+1) | out_edge(m) | in_off(n+1) | in_edge(m)]
     std::vector<size_t> adj_base;    // start of each class inside adj
     int max_nodes = 0;
+    std::vector<TcClassBlob> cblob_desc;  // per class
+    std::vector<unsigned char> cblob;     // all class blobs, each 16-byte aligned
+    int max_cblob_bytes = 0;
 };
 
 static inline int32_t tc_align16(int32_t x) { return (x + 15) & ~15; }
@@ -74,6 +77,27 @@ static inline std::string tc_pack_map(const TcMapDesc *map, TcPacked &pk) {
         for (int i = 0; i < n; i++) { oo[i + 1] += oo[i]; io[i + 1] += io[i]; }
         std::vector<int32_t> oc(oo.begin(), oo.end() - 1), ic(io.begin(), io.end() - 1);
         for (int e = 0; e < m; e++) { oe[oc[ed[2 * e]]++] = e; ie[ic[ed[2 * e + 1]]++] = e; }
+        {
+            TcClassBlob d;
+            d.n_nodes = n; d.n_edges = m;
+            int32_t o = 0;
+            auto sec = [&](int32_t bytes) { int32_t at = o; o = tc_align16(o + bytes); return at; };
+            sec(n * 16);
+            d.off_edges = sec(m * 8); d.off_out_off = sec((n + 1) * 4); d.off_out_edge = sec(m * 4);
+            d.off_in_off = sec((n + 1) * 4); d.off_in_edge = sec(m * 4);
+            d.bytes = o;
+            d.offset = (int32_t)pk.cblob.size();
+            pk.cblob.resize(pk.cblob.size() + (size_t)o, 0);
+            unsigned char *cb = pk.cblob.data() + d.offset;
+            memcpy(cb, map->ll_nodes + 2 * (size_t)map->ll_node_off[c], (size_t)n * 16);
+            memcpy(cb + d.off_edges, ed, (size_t)m * 8);
+            memcpy(cb + d.off_out_off, oo.data(), (size_t)(n + 1) * 4);
+            memcpy(cb + d.off_out_edge, oe.data(), (size_t)m * 4);
+            memcpy(cb + d.off_in_off, io.data(), (size_t)(n + 1) * 4);
+            memcpy(cb + d.off_in_edge, ie.data(), (size_t)m * 4);
+            pk.cblob_desc.push_back(d);
+            pk.max_cblob_bytes = std::max(pk.max_cblob_bytes, (int)o);
+        }
         pk.adj_base[c] = pk.adj.size();
         pk.adj.insert(pk.adj.end(), oo.begin(), oo.end());
         pk.adj.insert(pk.adj.end(), oe.begin(), oe.end());

@@ -29,10 +29,14 @@ class TinyCarloVecEnv:
     is_vector_env = True
 
     def __init__(self, config: Union[str, Dict[str, Any]], num_envs: int, device: Union[str, int, torch.device] = "cuda",
-                 obs_format: Optional[str] = None, env_index_offset: int = 0, spawn_table_len: int = 16, debug_segments: bool = False):
+                 obs_format: Optional[str] = None, env_index_offset: int = 0, spawn_table_len: Optional[int] = None,
+                 debug_segments: bool = False, autoreset: Optional[str] = None):
         """config: yaml path / directory / dict as for the reference env. num_envs: envs on THIS device.
         env_index_offset: global index of local env 0 (multi-GPU sharding: env i is seeded with seed + offset + i, so
-        results do not depend on how the envs are sharded). debug_segments: also export the projected int32 segments."""
+        results do not depend on how the envs are sharded). debug_segments: also export the projected int32 segments.
+        autoreset: None (the reference's behaviour: the caller resets finished envs, see reset(mask=...) / reset_done()) or
+        "next_step" (gymnasium's AutoresetMode.NEXT_STEP, done inside the step kernel with no extra launch: the step after an
+        env terminated or truncated resets it, ignores its action and returns the reset observation with reward 0)."""
         if not torch.cuda.is_available():
             raise _lib.TinyCarloError("TinyCarloVecEnv needs a CUDA device: there is no CPU implementation")
         self.config, self.config_path = load_config(config)
@@ -100,7 +104,10 @@ class TinyCarloVecEnv:
         self._upload_params()
 
         # ---- spawn draws (map.py:51-69): per-env numpy Generators seeded like gymnasium, pre-drawn K resets ahead
-        self._K = int(spawn_table_len)
+        if autoreset not in (None, "next_step"):
+            raise ValueError("autoreset must be None or 'next_step'")
+        self.autoreset = autoreset
+        self._K = int(spawn_table_len) if spawn_table_len else (64 if autoreset else 16)
         self._sampler = SpawnSampler(self.map, N, self._K, self.env_index_offset)
         self._spawn_table = None   # device int32 [N, K]
         self._spawn_cursor = None  # device int32 [N]
@@ -210,9 +217,24 @@ class TinyCarloVecEnv:
 
     def _upload_spawn_table(self, tab: np.ndarray):
         with torch.cuda.device(self.device):
-            self._spawn_table = torch.from_numpy(tab).to(self.device)
-            self._spawn_cursor = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+            if self._spawn_table is None:
+                self._spawn_table = torch.from_numpy(tab).to(self.device)
+                self._spawn_cursor = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+                if self.autoreset:
+                    # buffers registered with the library must keep their addresses: refills copy in place
+                    self.done_flags = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+                    _lib.check(self._L.tc_set_autoreset(self._h, _ptr(self.done_flags), _ptr(self._spawn_table), self._K,
+                                                        _ptr(self._spawn_cursor)), "tc_set_autoreset")
+            else:
+                self._spawn_table.copy_(torch.from_numpy(tab))
+                self._spawn_cursor.zero_()
         self._resets_since_refill = 0
+
+    def _refill_spawn_table_if_due(self):
+        """Each reset()/autoreset step consumes at most one pre-drawn spawn node per env; after K of them the cursors are
+        read back (the only host sync of the env, every K calls) and the consumed entries are replaced by fresh draws."""
+        if self._resets_since_refill >= self._K - 1:
+            self._upload_spawn_table(self._sampler.advance(self._spawn_cursor.cpu().numpy()))
 
     # ------------------------------------------------------------------------------------------------ gym-like API
     def _info(self) -> Dict[str, torch.Tensor]:
@@ -235,13 +257,14 @@ class TinyCarloVecEnv:
             if spawn_nodes is not None:
                 nodes = spawn_nodes.to(device=self.device, dtype=torch.int32).contiguous()
             else:
-                if self._resets_since_refill >= self._K:
-                    self._upload_spawn_table(self._sampler.advance(self._spawn_cursor.cpu().numpy()))
+                self._refill_spawn_table_if_due()
                 cur = self._spawn_cursor.long().clamp_(max=self._K - 1)
                 nodes = torch.gather(self._spawn_table, 1, cur[:, None])[:, 0].contiguous()
                 self._spawn_cursor += mask_u8.to(torch.int32)
                 self._resets_since_refill += 1
             self._spawn_nodes = nodes
+            if self.autoreset:
+                self.done_flags.masked_fill_(mask_u8.bool(), 0)
             outs = self._outs if not self.no_observation else self._outs_noobs
             _lib.check(self._L.tc_reset(self._h, _ptr(mask_u8), _ptr(nodes), C.byref(outs), self._stream()), "tc_reset")
         return self.obs, self._info()
@@ -259,14 +282,24 @@ class TinyCarloVecEnv:
             raise ValueError("action tensors must live on the env's device with shapes [N,2] and [N]")
         outs = self._outs if not self.no_observation else self._outs_noobs
         with torch.cuda.device(self.device):
+            if self.autoreset:
+                if not self._seeded:
+                    raise _lib.TinyCarloError("call reset() before step()")
+                self._refill_spawn_table_if_due()
+                self._resets_since_refill += 1
             _lib.check(self._L.tc_step(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
         o = self.out
         return self.obs, o["reward"], o["terminated"].view(torch.bool), o["truncated"].view(torch.bool), self._info()
 
     def reset_done(self):
-        """Auto-reset: resets the envs whose last step terminated or truncated (on the device, no host sync)."""
+        """Resets the envs whose last step terminated or truncated, as a caller of the reference would (on the device, no
+        host sync). With autoreset="next_step" this is unnecessary: the next step() does it inside the kernel."""
         done = self.out["terminated"] | self.out["truncated"]
         return self.reset(mask=done)
+
+    def mark_done(self, mask: torch.Tensor):
+        """autoreset only: ORs extra termination conditions (e.g. from wrappers) into the flags the next step() consumes."""
+        self.done_flags |= mask.to(device=self.device, dtype=torch.uint8)
 
     def step_host(self, car_control: torch.Tensor, maneuver: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor,
                   truncated: torch.Tensor, cte: Optional[torch.Tensor] = None, heading_error: Optional[torch.Tensor] = None):
@@ -274,6 +307,9 @@ class TinyCarloVecEnv:
         back, and the stream synchronised inside the call (tc_step_host). Observations stay on the device in self.obs."""
         outs = self._outs if not self.no_observation else self._outs_noobs
         with torch.cuda.device(self.device):
+            if self.autoreset:
+                self._refill_spawn_table_if_due()
+                self._resets_since_refill += 1
             _lib.check(self._L.tc_step_host(self._h, _ptr(car_control), _ptr(maneuver), C.byref(outs), _ptr(reward), _ptr(terminated),
                                             _ptr(truncated), _ptr(cte), _ptr(heading_error), self._stream()), "tc_step_host")
 
