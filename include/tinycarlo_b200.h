@@ -123,6 +123,8 @@ TC_API int tc_set_autoreset(TcHandle *h, uint8_t *dev_done /*[N]*/, const int32_
  * and zeroes their info outputs like the reference's reset (car.py:47-51). */
 TC_API int tc_reset(TcHandle *h, const uint8_t *dev_mask, const int32_t *dev_spawn_nodes, const TcOutputs *outs, void *stream);
 TC_API int tc_step(TcHandle *h, const float *dev_car_control /*[N,2]*/, const int32_t *dev_maneuver /*[N]*/, const TcOutputs *outs, void *stream);
+/* tc_step with float64 actions (the reference computes in float64 when it is fed Python floats). */
+TC_API int tc_step_f64(TcHandle *h, const double *dev_car_control /*[N,2]*/, const int32_t *dev_maneuver /*[N]*/, const TcOutputs *outs, void *stream);
 TC_API int tc_render(TcHandle *h, const uint8_t *dev_mask, uint8_t *dev_obs, int32_t obs_format, int32_t *dev_seg_count, int32_t *dev_seg_i32, void *stream);
 
 TC_API int tc_get_state(TcHandle *h, double *dev_sf /*[N,TC_SF_N]*/, int32_t *dev_si /*[N,TC_SI_N]*/, void *stream);

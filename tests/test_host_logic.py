@@ -1,0 +1,127 @@
+"""CPU tests of the host-side logic: config defaults, map tables, camera matrices, spawn draws, C-ABI symbols."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN_DIR, Golden
+from tinycarlo_b200 import _lib
+from tinycarlo_b200.camera_params import camera_row, extrinsic_matrix, intrinsic_matrix
+from tinycarlo_b200.config import camera_params, car_param_row, load_config, resolve_map_path, sim_params
+from tinycarlo_b200.maptables import MapTables
+from tinycarlo_b200.spawn import SpawnSampler
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SPAWN_KNUFF = [156, 18, 217, 214, 325, 354, 176, 402, 339, 376, 385, 419, 396, 37, 149, 62, 240, 113, 98, 299, 2]
+SPAWN_SIMPLE = [57, 143, 112, 121, 138, 157, 67, 46, 165, 124, 79, 33, 84, 21, 178, 7]
+
+
+def test_library_exports_every_declared_symbol():
+    """include/tinycarlo_b200.h <-> libtinycarlo_b200.so (no compute calls: there is no GPU here)."""
+    hdr = open(os.path.join(ROOT, "include", "tinycarlo_b200.h")).read()
+    declared = set(re.findall(r"TC_API\s+[\w\s\*]+?\b(tc_\w+)\s*\(", hdr))
+    assert len(declared) >= 18
+    _lib.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.tc_abi_version() == 1
+
+
+def test_product_has_no_cpu_path():
+    """Without a CUDA device the env refuses to construct (no fallback); the product never imports oracle/."""
+    import torch
+    if not torch.cuda.is_available():
+        from tinycarlo_b200 import TinyCarloVecEnv, TinyCarloError
+        with pytest.raises(TinyCarloError):
+            TinyCarloVecEnv({"sim": {}, "car": {}, "camera": {"max_range": 0.5}, "map": {"map_name": "simple_layout", "pixel_per_meter": 450}}, 2)
+    pkg = os.path.join(ROOT, "tinycarlo_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):   # the Python product never imports the oracle nor loads the host test build
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+                assert "tc_oracle" not in src and "hosttest" not in src, fn
+
+
+def test_config_defaults_and_errors(tmp_path):
+    cfg = {"sim": {}, "car": {}, "camera": {"max_range": 0.5}, "map": {"json_path": "m.json", "pixel_per_meter": 100}}
+    c, path = load_config(cfg)
+    assert path is None and sim_params(c) == {"fps": 30, "T": 1 / 30, "observation_space_format": "rgb", "render_realtime": False,
+                                                "overview_pixel_per_meter": 150, "render_node_names": False}
+    row = car_param_row(c["car"], 1 / 30)
+    assert row[:4] == [0.08, 0.03, 1.0, 35.0] and all(math.isnan(v) for v in row[4:7]) and row[7] == 1 / 30
+    cam = camera_params(c["camera"])
+    assert cam["resolution"] == [128, 160] and cam["fov"] == 90 and cam["line_thickness"] == 1 and cam["position"] == [0, 0, 0]
+    with pytest.raises(KeyError):
+        load_config({"sim": {}, "car": {}, "camera": {}})           # missing section -> KeyError like the reference
+    with pytest.raises(ValueError):
+        camera_params({})                                            # max_range None: the reference crashes on the first frame
+    with pytest.raises(TypeError):
+        car_param_row({"max_acceleration": 0.1}, 1 / 30)            # car.py:82 `None * dt`
+    # yaml path and directory forms; json_path relative to the yaml (map.py:15-16)
+    (tmp_path / "config.yaml").write_text("sim: {fps: 20}\ncar: {}\ncamera: {max_range: 1.0}\nmap: {json_path: maps/x.json, pixel_per_meter: 10}\n")
+    for arg in (str(tmp_path / "config.yaml"), str(tmp_path)):
+        c, path = load_config(arg)
+        assert c["sim"]["fps"] == 20 and path == str(tmp_path / "config.yaml")
+        assert resolve_map_path(c["map"], path) == str(tmp_path / "maps/x.json")
+    assert resolve_map_path({"json_path": "a/b.json"}, None) == "./a/b.json"
+
+
+def test_map_tables_follow_the_reference_loader():
+    t = MapTables(resolve_map_path({"map_name": "knuffingen"}, None), 222, SPAWN_KNUFF)
+    assert t.class_names == ["outer", "dashed", "solid", "hold", "area"]
+    assert list(np.diff(t.ll_node_off)) == [517, 111, 149, 18, 32] and list(np.diff(t.ll_edge_off)) == [499, 81, 116, 11, 32]
+    assert t.lp_nodes.shape == (429, 2) and t.lp_edges.shape == (443, 2)
+    import json
+    raw = json.load(open(resolve_map_path({"map_name": "knuffingen"}, None)))
+    n0 = raw["lanepath"]["nodes"][113]
+    assert t.lp_nodes[113][0] == n0[0] / 222 and t.lp_nodes[113][1] == n0[1] / 222   # SURVEY Appendix B spawn node
+    assert list(t.lp_nodes[113]) == [4.202702702702703, 0.8153153153153153]
+    e = np.nonzero(t.lp_edges[:, 0] == 113)[0][0]
+    assert t.lp_orient[e] == -0.3268266529299409
+    assert np.allclose(np.abs(np.abs(t.lp_orient - t.lp_orient_rev) - math.pi), 0, atol=1e-12)
+    assert int((~t.has_successor).sum()) == 6
+
+
+def test_camera_matrices_match_reference_values():
+    """E and K of the shipped Knuffingen camera at 480x640, recorded from the live reference."""
+    E = extrinsic_matrix([0.0, -0.005, 0.04], [22, 0, 0])
+    want = [[6.123233995736766e-17, -1, 0, -0.005], [0.37460659341591196, 2.2938038278314527e-17, 0.9271838545667874, -0.0370873541826715],
+            [-0.9271838545667874, -5.677363698581607e-17, 0.37460659341591196, -0.01498426373663648]]
+    np.testing.assert_allclose(E, np.array(want), rtol=1e-15, atol=1e-17)
+    assert np.array_equal(E, Golden("knuff_480_stanley")["E"][0])   # bit for bit what the reference computed
+    K = intrinsic_matrix(80, [480, 640])
+    assert K[0, 0] == 381.3611496301472 and K[1, 1] == 286.02086222261045 and K[0, 2] == 320 and K[1, 2] == 240
+    for name in ("knuff_camrand",):
+        g = Golden(name)
+        muts = {int(k): v for k, v in g.meta["cam_mutations"].items()}
+        cc = dict(g.cfg["camera"])
+        for f in range(g.F):
+            t = int(g["ev_step"][f])
+            if g["ev_kind"][f] == 1 and t in muts:
+                cc.update(muts[t])
+            row = camera_row(cc["position"], cc["orientation"], cc["fov"], cc["resolution"], cc["max_range"])
+            if g["ev_kind"][f] == 1:
+                assert np.array_equal(row[:12].reshape(3, 4), g["E"][f]), f
+                assert row[12] == g["K"][f][0][0] and row[13] == g["K"][f][1][1]
+
+
+def test_spawn_sampler_matches_reference_draws():
+    d = np.load(os.path.join(GOLDEN_DIR, "spawn_draws.npz"))
+    for key, (mname, ppm, sp) in {"knuffingen_default": ("knuffingen", 222, SPAWN_KNUFF), "knuffingen_none": ("knuffingen", 222, None),
+                                  "simple_layout_default": ("simple_layout", 450, SPAWN_SIMPLE), "simple_layout_none": ("simple_layout", 450, None)}.items():
+        t = MapTables(resolve_map_path({"map_name": mname}, None), ppm, sp)
+        want = d[key]                      # [64 seeds, 12 consecutive resets]
+        # a vector env seeded with s gives env i the reference's stream for seed s + i
+        s = SpawnSampler(t, 16, table_len=5, env_index_offset=3)
+        tab = s.seed(10)
+        assert np.array_equal(tab, want[13:29, :5]), key
+        # consuming entries and refilling continues each env's stream
+        consumed = np.array([i % 4 for i in range(16)])
+        tab = s.advance(consumed).copy()
+        for i in range(16):
+            assert np.array_equal(tab[i], want[13 + i, consumed[i]:consumed[i] + 5]), (key, i)

@@ -302,12 +302,12 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
 }
 
 static int tc_launch_track(TcHandle *h, int mode, const float *cc, const int32_t *man, const uint8_t *mask, const int32_t *spawn,
-                           const TcOutputs *outs, cudaStream_t st) {
+                           const TcOutputs *outs, cudaStream_t st, const double *cc64 = nullptr) {
     TcTrackArgs ta;
     memset(&ta, 0, sizeof(ta));
     ta.blob = h->d_blob; ta.layout = h->layout; ta.n_envs = h->n_envs; ta.mode = mode; ta.wrapped = h->wrapped;
     ta.sf = h->d_sf; ta.si = h->d_si; ta.car = h->d_car; ta.cam = h->d_cam; ta.pose = h->d_pose;
-    ta.act_cc = cc; ta.act_man = man; ta.mask = mask; ta.spawn_nodes = spawn;
+    ta.act_cc = cc; ta.act_cc64 = cc64; ta.act_man = man; ta.mask = mask; ta.spawn_nodes = spawn;
     ta.done = h->ar_done; ta.spawn_table = h->ar_table; ta.spawn_cursor = h->ar_cursor; ta.spawn_k = h->ar_k;
     if (outs) ta.out = *outs;
     const int envs_per_block = TC_TRACK_THREADS / 32;
@@ -328,15 +328,29 @@ int tc_reset(TcHandle *h, const uint8_t *dev_mask, const int32_t *dev_spawn_node
     return TC_OK;
 }
 
+static int tc_step_impl(TcHandle *h, const float *dev_car_control, const double *dev_car_control64, const int32_t *dev_maneuver,
+                        const TcOutputs *outs, void *stream);
+
 int tc_step(TcHandle *h, const float *dev_car_control, const int32_t *dev_maneuver, const TcOutputs *outs, void *stream) {
-    if (!h || !dev_car_control || !dev_maneuver) return tc_fail(TC_ERR_INVALID, "tc_step: null argument");
+    if (!dev_car_control) return tc_fail(TC_ERR_INVALID, "tc_step: null argument");
+    return tc_step_impl(h, dev_car_control, nullptr, dev_maneuver, outs, stream);
+}
+
+int tc_step_f64(TcHandle *h, const double *dev_car_control, const int32_t *dev_maneuver, const TcOutputs *outs, void *stream) {
+    if (!dev_car_control) return tc_fail(TC_ERR_INVALID, "tc_step_f64: null argument");
+    return tc_step_impl(h, nullptr, dev_car_control, dev_maneuver, outs, stream);
+}
+
+static int tc_step_impl(TcHandle *h, const float *dev_car_control, const double *dev_car_control64, const int32_t *dev_maneuver,
+                        const TcOutputs *outs, void *stream) {
+    if (!h || !dev_maneuver) return tc_fail(TC_ERR_INVALID, "tc_step: null argument");
     if (!h->car_set || !h->cam_set) return tc_fail(TC_ERR_STATE, "tc_step: car/camera parameters not set");
     TC_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const bool prof = h->profiling && h->prof_used < h->prof_cap;
     cudaEvent_t *ev = prof ? &h->prof_ev[(size_t)4 * h->prof_used] : nullptr;
     if (prof) TC_CUDA(cudaEventRecord(ev[0], st));
-    TC_TRY(tc_launch_track(h, 0, dev_car_control, dev_maneuver, nullptr, nullptr, outs, st));
+    TC_TRY(tc_launch_track(h, 0, dev_car_control, dev_maneuver, nullptr, nullptr, outs, st, dev_car_control64));
     if (prof) TC_CUDA(cudaEventRecord(ev[1], st));
     if (outs && (outs->obs || outs->seg_count || outs->seg_i32))
         TC_TRY(tc_launch_render(h, nullptr, outs->obs, h->obs_format, outs->seg_count, outs->seg_i32, st, prof ? ev[2] : nullptr));

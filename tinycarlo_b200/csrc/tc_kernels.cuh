@@ -60,6 +60,7 @@ struct TcTrackArgs {
     const double *cam;   // [N, TC_CAM_N]
     double *pose;        // [N, 12] out
     const float *act_cc; // [N,2]
+    const double *act_cc64; // [N,2] optional float64 actions (single-env drop-in: Python-float actions keep full precision)
     const int32_t *act_man;
     const uint8_t *mask;        // reset: envs to reset (NULL = all)
     const int32_t *spawn_nodes; // reset
@@ -112,7 +113,9 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS) tc_track_kernel(const TcTrac
     } else {
         tc_load_state(sf, si, s);
         // env.py:118: np.clip(action["car_control"], -1, 1) on float64
-        double v_cmd = tc_np_clip((double)a.act_cc[2 * env], -1.0, 1.0), s_cmd = tc_np_clip((double)a.act_cc[2 * env + 1], -1.0, 1.0);
+        double v_raw = a.act_cc64 ? a.act_cc64[2 * env] : (double)a.act_cc[2 * env];
+        double s_raw = a.act_cc64 ? a.act_cc64[2 * env + 1] : (double)a.act_cc[2 * env + 1];
+        double v_cmd = tc_np_clip(v_raw, -1.0, 1.0), s_cmd = tc_np_clip(s_raw, -1.0, 1.0);
         truncated = tc_car_step(g, t, cp, s, v_cmd, s_cmd, a.act_man[env]);
     }
     double dist[TC_MAX_CLASSES];

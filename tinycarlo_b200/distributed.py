@@ -1,0 +1,37 @@
+"""Multi-GPU plumbing. Environments are independent, so a job of `total_envs` is sharded by env index with NO per-step
+collective: rank r owns the contiguous range shard_range(total, r, world), seeds its envs with their GLOBAL index
+(TinyCarloVecEnv(env_index_offset=...)), and the only communication is an all-gather of a few episode statistics at log
+cadence (NCCL over NVLink on the GPUs, gloo in the CPU tests)."""
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total_envs: int, rank: int, world: int) -> Tuple[int, int]:
+    """[start, stop) of the envs owned by `rank`; the first total % world ranks get one extra env."""
+    base, extra = divmod(int(total_envs), int(world))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+class EpisodeStats:
+    """Per-rank running episode statistics on the device: episodes finished, truncations, reward sum, env-steps."""
+    FIELDS = ("episodes", "truncated", "reward_sum", "env_steps")
+
+    def __init__(self, device):
+        self.local = torch.zeros(len(self.FIELDS), dtype=torch.float64, device=device)
+
+    def update(self, reward: torch.Tensor, terminated: torch.Tensor, truncated: torch.Tensor):
+        self.local[0] += (terminated | truncated).sum()
+        self.local[1] += truncated.sum()
+        self.local[2] += reward.sum()
+        self.local[3] += reward.numel()
+
+    def gather(self) -> torch.Tensor:
+        """[world, 4] on every rank (all_gather_into_tensor: NCCL over NVLink / NVSwitch on GPUs)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self.local[None].clone()
+        out = torch.zeros((dist.get_world_size(), len(self.FIELDS)), dtype=torch.float64, device=self.local.device)
+        dist.all_gather_into_tensor(out, self.local)
+        return out

@@ -274,7 +274,8 @@ class TinyCarloVecEnv:
         int [N]. Returns (obs, reward f32[N], terminated bool[N], truncated bool[N], info dict of tensors)."""
         cc = action["car_control"]
         man = action["maneuver"]
-        if cc.dtype != torch.float32 or not cc.is_contiguous():
+        f64 = cc.dtype == torch.float64   # float64 actions keep the reference's float64 path bit for bit
+        if (cc.dtype not in (torch.float32, torch.float64)) or not cc.is_contiguous():
             cc = cc.to(torch.float32).contiguous()
         if man.dtype != torch.int32 or not man.is_contiguous():
             man = man.to(torch.int32).contiguous()
@@ -287,7 +288,8 @@ class TinyCarloVecEnv:
                     raise _lib.TinyCarloError("call reset() before step()")
                 self._refill_spawn_table_if_due()
                 self._resets_since_refill += 1
-            _lib.check(self._L.tc_step(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
+            fn = self._L.tc_step_f64 if f64 else self._L.tc_step
+            _lib.check(fn(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
         o = self.out
         return self.obs, o["reward"], o["terminated"].view(torch.bool), o["truncated"].view(torch.bool), self._info()
 
