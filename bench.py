@@ -166,7 +166,7 @@ def main():
     cc = torch.zeros((N, 2), dtype=torch.float32, device=dev)
     cc[:, 0] = speed
     stats = torch.zeros(4, dtype=torch.float64, device=dev)  # episodes finished, truncations, reward sum, env-steps
-    gathered = torch.zeros((world, 4), dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = torch.zeros(world * 4, dtype=torch.float64, device=dev) if world > 1 else None
 
     env.reset(seed=0)
 

@@ -32,6 +32,6 @@ class EpisodeStats:
         """[world, 4] on every rank (all_gather_into_tensor: NCCL over NVLink / NVSwitch on GPUs)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return self.local[None].clone()
-        out = torch.zeros((dist.get_world_size(), len(self.FIELDS)), dtype=torch.float64, device=self.local.device)
+        out = torch.zeros(dist.get_world_size() * len(self.FIELDS), dtype=torch.float64, device=self.local.device)
         dist.all_gather_into_tensor(out, self.local)
-        return out
+        return out.view(dist.get_world_size(), len(self.FIELDS))
