@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                                           str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -185,12 +185,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # sampled from the warm-up to the end of the device-timed region (all under load)
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = env.launch_count
     env.profile_begin(args.steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -241,6 +241,15 @@ def main():
                "d2h_bytes_per_step": N * 14, "note": "tc_step_host: pinned host actions in, reward/terminated/truncated/cte/heading out; "
                "observations stay in HBM (the vectorised entry point returns CUDA tensors)"}
 
+    # for context next to the copy peak: torch's own fill kernel zeroing the same observation tensor
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    write_ceiling = 0.0
+    for _ in range(3):
+        w0.record()
+        env.obs.zero_()
+        w1.record()
+        torch.cuda.synchronize(dev)
+        write_ceiling = max(write_ceiling, env.obs.numel() / (w0.elapsed_time(w1) * 1e-3) / 1e9)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -259,7 +268,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": "tc_render_classes_kernel", "kernel_ms_per_launch": raster_ms,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "step_share": {k: v / max(kern_steps, 1) for k, v in kern_ms.items()}}
+                "step_share_ms": {k: v / max(kern_steps, 1) for k, v in kern_ms.items()},
+                "torch_zero_fill_gbs": write_ceiling}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

@@ -295,3 +295,43 @@ def test_cuda_autoreset_next_step_matches_oracle():
         assert np.array_equal(env.done_flags.cpu().numpy().astype(bool), done)
     assert n_resets > 0
     env.close()
+
+
+def test_cuda_full_size_properties():
+    """BASELINE.json's headline size (16384 envs, Knuffingen, 5x480x640 classes = 25 GB of observations), checked through
+    size-independent properties plus a sample of envs against the oracle."""
+    n, reps = 16384, 256
+    cfg = make_config("knuffingen", "classes", cam={"resolution": [480, 640]})
+    env = _vec(cfg, n)
+    rng = np.random.default_rng(2024)
+    # env i and env i + k*reps share spawn node and actions -> must stay identical (replication invariance)
+    spawn_pool = np.array(cfg["map"]["spawn_points"], np.int32)
+    spawn = np.tile(spawn_pool[rng.integers(0, len(spawn_pool), reps)], n // reps)
+    env.reset(seed=0, spawn_nodes=torch.from_numpy(spawn))
+    sample = np.arange(0, reps, 8)                                   # 32 distinct envs checked against the oracle
+    oenv = oracle_env(cfg, len(sample))
+    oenv.reset(spawn[sample])
+    man = np.tile(rng.integers(0, 4, reps).astype(np.int32), n // reps)
+    for t in range(6):
+        cc = np.tile(np.stack([rng.uniform(0.3, 1, reps), rng.uniform(-1, 1, reps)], 1).astype(np.float32), (n // reps, 1))
+        obs, reward, term, trunc, info = env.step({"car_control": torch.from_numpy(cc).cuda(), "maneuver": torch.from_numpy(man).cuda()})
+        oenv.step(cc[sample].astype(np.float64), man[sample])
+        assert np.array_equal(obs[torch.from_numpy(sample).cuda()].cpu().numpy(), oenv.obs), t
+        np.testing.assert_allclose(env.out["info_f64"][torch.from_numpy(sample).cuda()].cpu().numpy(), oenv.info, rtol=RTOL64, atol=1e-11)
+    # only 0 / 255 and replicas identical — in chunks of `reps` envs, so that the temporaries stay small next to the 25 GB tensor
+    first = obs[:reps]
+    total_px = 0
+    for k in range(n // reps):
+        chunk = obs[k * reps:(k + 1) * reps]
+        assert torch.equal(chunk, first), f"replica block {k} diverged"
+        if k % 8 == 0:
+            assert bool(((chunk == 0) | (chunk == 255)).all())
+            total_px += int((chunk > 0).sum())
+    assert total_px > 0
+    # re-rendering the same poses is idempotent, and the RGB render marks exactly the union of the class masks
+    keep = obs[:512].clone()
+    env.render_obs()
+    assert torch.equal(obs[:512], keep) and torch.equal(obs[n - reps:], first)
+    rgb = env.render_rgb()[:64]
+    assert torch.equal((rgb > 0).any(dim=3), (obs[:64] > 0).any(dim=1))
+    env.close()
