@@ -231,9 +231,14 @@ def main():
             step_host()
         barrier()
         t0 = time.perf_counter()
+        per_step = []
         for _ in range(args.steps):
+            ts = time.perf_counter()
             step_host()
+            per_step.append(time.perf_counter() - ts)
         torch.cuda.synchronize(dev)
+        if os.environ.get("TC_BENCH_DEBUG") and rank == 0:
+            print("e2e per-step ms:", [round(x * 1e3, 2) for x in per_step], file=sys.stderr)
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)

@@ -335,3 +335,39 @@ def test_cuda_full_size_properties():
     rgb = env.render_rgb()[:64]
     assert torch.equal((rgb > 0).any(dim=3), (obs[:64] > 0).any(dim=1))
     env.close()
+
+
+def test_cuda_checkpoint_restore_resumes_bit_for_bit():
+    """checkpoint() / restore(): a rollout resumed in a fresh env continues exactly (state, spawn streams, autoreset flags)."""
+    n = 2048
+    cfg = make_config("simple_layout", "classes", cam={"resolution": [84, 84]}, car={"max_velocity": 0.15})
+    rng = np.random.default_rng(5)
+    acts = [(torch.from_numpy(rng.uniform(-1, 1, (n, 2)).astype(np.float32)).cuda(), torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)).cuda())
+            for _ in range(90)]
+    env = _vec(cfg, n, autoreset="next_step", spawn_table_len=4)
+    env.reset(seed=77)
+    for cc, man in acts[:40]:
+        env.step({"car_control": cc, "maneuver": man})
+    ck = env.checkpoint()
+    tail_a = []
+    force = {k: torch.from_numpy(rng.random(n) < 0.1).cuda() for k in (3, 4, 5, 20, 33)}   # forced episode ends -> spawn draws
+    for k, (cc, man) in enumerate(acts[40:]):
+        if k in force:
+            env.mark_done(force[k])
+        obs, r, te, tr, _ = env.step({"car_control": cc, "maneuver": man})
+        tail_a.append((obs.clone(), r.clone(), te.clone(), tr.clone(), env.out["info_f64"].clone()))
+    env.close()
+    env2 = _vec(cfg, n, autoreset="next_step", spawn_table_len=4)
+    env2.reset(seed=1)          # different streams, then overwritten by the checkpoint
+    env2.restore(ck)
+    for k, ((cc, man), want) in enumerate(zip(acts[40:], tail_a)):
+        if k in force:
+            env2.mark_done(force[k])
+        obs, r, te, tr, _ = env2.step({"car_control": cc, "maneuver": man})
+        assert torch.equal(env2.out["info_f64"], want[4]), "info"
+        assert torch.equal(te, want[2]) and torch.equal(tr, want[3]), "flags"
+        assert torch.equal(r, want[1]), "reward"
+        assert torch.equal(obs, want[0]), "obs"
+
+    assert int(env2._spawn_cursor.sum()) + env2._resets_since_refill > 0
+    env2.close()

@@ -125,3 +125,33 @@ def test_spawn_sampler_matches_reference_draws():
         tab = s.advance(consumed).copy()
         for i in range(16):
             assert np.array_equal(tab[i], want[13 + i, consumed[i]:consumed[i] + 5]), (key, i)
+
+
+def test_vectorised_pcg64_equals_numpy_generator():
+    """tinycarlo_b200/pcg64.py against numpy itself: SeedSequence pool, raw PCG64 outputs, buffered 32-bit halves and
+    Lemire-bounded integers (incl. ranges with ~50 % rejection), for small and multi-word seeds, with masks."""
+    from tinycarlo_b200.pcg64 import VecPCG64, seed_sequence_state
+    seeds = np.array(list(range(0, 200)) + [2**32 - 1, 2**32, 2**32 + 5, 2**40 + 123, 2**63 + 7, 2**64 - 1, 123456789012], dtype=np.uint64)
+    ss = seed_sequence_state(seeds)
+    for i, s in enumerate(seeds):
+        assert np.array_equal(ss[i], np.random.SeedSequence(int(s)).generate_state(4, np.uint64)), int(s)
+    v = VecPCG64(seeds)
+    bg = [np.random.PCG64(np.random.SeedSequence(int(s))) for s in seeds]
+    everyone = np.ones(len(seeds), bool)
+    for _ in range(4):
+        assert np.array_equal(v.next_uint64(everyone), np.array([b.random_raw() for b in bg], dtype=np.uint64))
+    v = VecPCG64(seeds)
+    gens = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(int(s)))) for s in seeds]
+    for hi in [21, 16, 429, 428, 2**31 + 1, 3, 2**32, 1, 7, 100000, 21]:
+        assert np.array_equal(v.bounded(hi), np.array([int(g.integers(0, hi)) for g in gens])), hi
+    lst = list(range(100, 121))
+    mask = np.arange(len(seeds)) % 3 == 0
+    got = np.array(lst)[v.bounded(len(lst), mask)]
+    assert np.array_equal(got, np.array([int(g.choice(lst)) for g, m in zip(gens, mask) if m]))
+    assert np.array_equal(v.bounded(428), np.array([int(g.integers(0, 428, size=1, dtype=int)[0]) for g in gens]))
+    # checkpoint round trip
+    st = v.state_dict()
+    a = v.bounded(1000)
+    w = VecPCG64()
+    w.load_state_dict(st)
+    assert np.array_equal(w.bounded(1000), a)

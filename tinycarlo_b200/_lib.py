@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libtinycarlo_b200.so")
+LIB_PATH = os.environ.get("TC_LIB") or os.path.join(LIB_DIR, "libtinycarlo_b200.so")   # TC_LIB: A/B test another build
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
 

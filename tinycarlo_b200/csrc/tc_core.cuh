@@ -598,20 +598,28 @@ TC_HD int tc_setup_line2(int W, int H, int64_t x1, int64_t y1, int64_t x2, int64
 enum { TC_SLOT_EDGE0 = 0, TC_SLOT_SPAN0 = 4, TC_SLOT_CAP0 = 10 };
 enum { TC_ROLE_SPANS = 0, TC_ROLE_EDGE0 = 1 /* ..4 */, TC_ROLE_CAPS = 5, TC_N_ROLES = 6, TC_ROLE_ALL = -1 };
 
+// 4-way select instead of a runtime-indexed local array (which would live in local memory: on the GPU every such access
+// queues behind the observation stores in the load/store pipeline)
+TC_HD int64_t tc_sel4(int i, int64_t a, int64_t b, int64_t c, int64_t d) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : d)); }
+
 TC_HD void tc_setup_fill_convex_poly4(int W, int H, const int64_t (*v)[2], int role, TcPrim *out) {
     const int npts = 4;
     const int64_t delta = TC_XY_ONE >> 1;
+    const int64_t vx0 = v[0][0], vx1 = v[1][0], vx2 = v[2][0], vx3 = v[3][0];
+    const int64_t vy0 = v[0][1], vy1 = v[1][1], vy2 = v[2][1], vy3 = v[3][1];
     int imin = 0, edges = npts;
-    int64_t xmin = v[0][0], xmax = v[0][0], ymin = v[0][1], ymax = v[0][1];
-    int64_t p0x = v[npts - 1][0], p0y = v[npts - 1][1];
-    for (int i = 0; i < npts; i++) {
-        if (v[i][1] < ymin) { ymin = v[i][1]; imin = i; }
-        if (v[i][1] > ymax) ymax = v[i][1];
-        if (v[i][0] > xmax) xmax = v[i][0];
-        if (v[i][0] < xmin) xmin = v[i][0];
-        if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + i) tc_setup_line2(W, H, p0x, p0y, v[i][0], v[i][1], out + TC_SLOT_EDGE0 + i);
-        p0x = v[i][0]; p0y = v[i][1];
-    }
+    int64_t xmin = vx0, xmax = vx0, ymin = vy0, ymax = vy0;
+    if (vy1 < ymin) { ymin = vy1; imin = 1; }
+    if (vy2 < ymin) { ymin = vy2; imin = 2; }
+    if (vy3 < ymin) { ymin = vy3; imin = 3; }
+    ymax = vy1 > ymax ? vy1 : ymax; ymax = vy2 > ymax ? vy2 : ymax; ymax = vy3 > ymax ? vy3 : ymax;
+    xmax = vx1 > xmax ? vx1 : xmax; xmax = vx2 > xmax ? vx2 : xmax; xmax = vx3 > xmax ? vx3 : xmax;
+    xmin = vx1 < xmin ? vx1 : xmin; xmin = vx2 < xmin ? vx2 : xmin; xmin = vx3 < xmin ? vx3 : xmin;
+    // outline: edge i runs from vertex i-1 to vertex i (the closing edge first)
+    if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + 0) tc_setup_line2(W, H, vx3, vy3, vx0, vy0, out + TC_SLOT_EDGE0 + 0);
+    if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + 1) tc_setup_line2(W, H, vx0, vy0, vx1, vy1, out + TC_SLOT_EDGE0 + 1);
+    if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + 2) tc_setup_line2(W, H, vx1, vy1, vx2, vy2, out + TC_SLOT_EDGE0 + 2);
+    if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + 3) tc_setup_line2(W, H, vx2, vy2, vx3, vy3, out + TC_SLOT_EDGE0 + 3);
     if (role != TC_ROLE_ALL && role != TC_ROLE_SPANS) return;
     int k = TC_SLOT_SPAN0;
     xmin = (xmin + delta) >> TC_XY_SHIFT; xmax = (xmax + delta) >> TC_XY_SHIFT;
@@ -619,33 +627,36 @@ TC_HD void tc_setup_fill_convex_poly4(int W, int H, const int64_t (*v)[2], int r
     if ((int)xmax < 0 || (int)ymax < 0 || (int)xmin >= W || (int)ymin >= H) return;
     if (ymax > H - 1) ymax = H - 1;
     int y = (int)ymin;
-    int e_idx[2] = {imin, imin}, e_di[2] = {1, npts - 1}, e_ye[2] = {y, y};
-    int64_t e_x[2] = {-TC_XY_ONE, -TC_XY_ONE}, e_dx[2] = {0, 0};
+    // the two scan-line walkers (kept in scalars: e?0 walks the vertices upwards, e?1 downwards)
+    int idxA = imin, idxB = imin, yeA = y, yeB = y;
+    int64_t xA = -TC_XY_ONE, xB = -TC_XY_ONE, dxA = 0, dxB = 0;
     while (true) {
-        for (int i = 0; i < 2; i++) {
-            if (y >= e_ye[i]) {
-                int idx0 = e_idx[i], di = e_di[i];
-                int idx = idx0 + di;
-                if (idx >= npts) idx -= npts;
-                for (; edges-- > 0;) {
-                    int ty = (int)((v[idx][1] + delta) >> TC_XY_SHIFT);
-                    if (ty > y) {
-                        int64_t xs = v[idx0][0], xe = v[idx][0];
-                        e_ye[i] = ty;
-                        e_dx[i] = tc_div_trunc((xe - xs) * 2 + (ty - y), 2 * (ty - y));
-                        e_x[i] = xs;
-                        e_idx[i] = idx;
-                        break;
-                    }
-                    idx0 = idx;
-                    idx += di;
-                    if (idx >= npts) idx -= npts;
-                }
-            }
+#define TC_WALK(IDX, YE, X, DX, DI)                                                        \
+        if (y >= YE) {                                                                     \
+            int idx0 = IDX;                                                                \
+            int idx = idx0 + DI;                                                           \
+            if (idx >= npts) idx -= npts;                                                  \
+            for (; edges-- > 0;) {                                                         \
+                int ty = (int)((tc_sel4(idx, vy0, vy1, vy2, vy3) + delta) >> TC_XY_SHIFT); \
+                if (ty > y) {                                                              \
+                    int64_t xs = tc_sel4(idx0, vx0, vx1, vx2, vx3), xe = tc_sel4(idx, vx0, vx1, vx2, vx3); \
+                    YE = ty;                                                               \
+                    DX = tc_div_trunc((xe - xs) * 2 + (ty - y), 2 * (ty - y));             \
+                    X = xs;                                                                \
+                    IDX = idx;                                                             \
+                    break;                                                                 \
+                }                                                                          \
+                idx0 = idx;                                                                \
+                idx += DI;                                                                 \
+                if (idx >= npts) idx -= npts;                                              \
+            }                                                                              \
         }
+        TC_WALK(idxA, yeA, xA, dxA, 1)
+        TC_WALK(idxB, yeB, xB, dxB, (npts - 1))
+#undef TC_WALK
         if (edges < 0) break;
         // rows y .. y_end-1 share the walker state: the next event is the smaller ye (both are > y here), capped by ymax
-        int y_end = e_ye[0] < e_ye[1] ? e_ye[0] : e_ye[1];
+        int y_end = yeA < yeB ? yeA : yeB;
         if (y_end > (int)ymax + 1) y_end = (int)ymax + 1;
         if (y_end <= y) y_end = y + 1;
         int r0 = y < 0 ? 0 : y;
@@ -653,10 +664,10 @@ TC_HD void tc_setup_fill_convex_poly4(int W, int H, const int64_t (*v)[2], int r
             TcPrim &q = out[k++];
             q.kind = TC_PRIM_SPAN;
             q.a[0] = y; q.a[1] = r0; q.a[2] = y_end;
-            q.a[3] = (int32_t)e_x[0]; q.a[4] = (int32_t)e_dx[0]; q.a[5] = (int32_t)e_x[1]; q.a[6] = (int32_t)e_dx[1];
+            q.a[3] = (int32_t)xA; q.a[4] = (int32_t)dxA; q.a[5] = (int32_t)xB; q.a[6] = (int32_t)dxB;
         }
-        e_x[0] += (int64_t)(y_end - y) * e_dx[0];
-        e_x[1] += (int64_t)(y_end - y) * e_dx[1];
+        xA += (int64_t)(y_end - y) * dxA;
+        xB += (int64_t)(y_end - y) * dxB;
         y = y_end;
         if (y > (int)ymax) break;
     }

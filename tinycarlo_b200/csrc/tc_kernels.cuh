@@ -455,10 +455,14 @@ __host__ __device__ inline size_t tc_render_smem_bytes(int max_nodes, int max_ed
            (size_t)TC_SETUP_CHUNK * TC_MAX_PRIMS_PER_SEG * sizeof(TcPrim);
 }
 
-__global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_render_classes_kernel(const TcRenderArgs a) {
+#ifndef TC_RENDER_MIN_BLOCKS
+#define TC_RENDER_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(TC_RASTER_THREADS, TC_RENDER_MIN_BLOCKS) tc_render_classes_kernel(const TcRenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int seg_cnt;
     __shared__ __align__(8) uint64_t bar;
+    __shared__ double s_pose[12], s_cam[TC_CAM_N];
     const int env = blockIdx.x / a.n_classes, c = blockIdx.x % a.n_classes;
     if (a.mask && !a.mask[env]) return;
     const int tid = threadIdx.x;
@@ -478,8 +482,15 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_render_classes_kernel
             } while (t1 - t0 < (unsigned long long)slot * a.stagger_ns);
         }
     }
-    long long tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0, tl_setup = 0, tl_draw = 0, tl_z = 0;
-    if (a.timeline && tid == 0) tl0 = clock64();
+// per-block phase clocks for tools/timeline.py: compiled in only with -DTC_TIMELINE (the seven 64-bit counters cost
+// registers and spills in the production build)
+#ifdef TC_TIMELINE
+#define TC_TL(stmt) do { if (a.timeline && tid == 0) { stmt; } } while (0)
+    long long tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0, tl_setup = 0, tl_draw = 0, tl_z = 0, tc0 = 0;
+#else
+#define TC_TL(stmt) do { } while (0)
+#endif
+    TC_TL(tl0 = clock64());
     const TcClassBlob cb = a.cblob_desc[c];
     unsigned char *tab_smem = smem_raw + tc_render_scratch_bytes(a.max_nodes);
     if (tid == 0) {
@@ -499,15 +510,15 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_render_classes_kernel
         sc.ix = (int32_t *)(sc.Pz + np); sc.iy = sc.ix + np;
         uint8_t *fA = (uint8_t *)(sc.iy + np), *fB = fA + np, *rA = fB + np, *rB = rA + np;
         sc.vis = rB + np; sc.front = fA; sc.inr = rA;
-        double pose[12], cam[TC_CAM_N];
-#pragma unroll
-        for (int i = 0; i < 12; i++) pose[i] = a.pose[(size_t)env * 12 + i];
-#pragma unroll
-        for (int i = TC_CAM_FX; i <= TC_CAM_MAX_RANGE; i++) cam[i] = a.cam[(size_t)env * TC_CAM_N + i];
+        // pose and intrinsics go through shared memory: 17 doubles held in registers by every thread across the whole
+        // camera pass would push the kernel over 64 registers, and spills are local-memory traffic behind the stores
+        if (tid < 12) s_pose[tid] = a.pose[(size_t)env * 12 + tid];
+        else if (tid < 12 + (TC_CAM_MAX_RANGE - TC_CAM_FX + 1)) s_cam[TC_CAM_FX + tid - 12] = a.cam[(size_t)env * TC_CAM_N + TC_CAM_FX + tid - 12];
+        __syncthreads();      // barrier init, pose and intrinsics visible to all threads
+        const double *pose = s_pose, *cam = s_cam;
         const double max_range = cam[TC_CAM_MAX_RANGE];
-        __syncthreads();      // barrier init visible to all threads
         tc_mbar_wait(&bar, 0); // the class's tables have landed in shared memory
-        if (a.timeline && tid == 0) tl1 = clock64();
+        TC_TL(tl1 = clock64());
         const TcClassTables ct = tc_class_tables_from_blob(tab_smem, cb);
         for (int v = tid; v < n; v += TC_RASTER_THREADS) {
             double X, Y, Z;
@@ -542,13 +553,13 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_render_classes_kernel
         __syncthreads(); // scratch and tables are dead from here on; the plane takes their place
     }
     const int cnt = seg_cnt;
-    if (a.timeline && tid == 0) tl2 = clock64();
+    TC_TL(tl2 = clock64());
     uint8_t *out = a.obs + ((size_t)env * a.n_classes + c) * a.H * a.W;
     const size_t nbytes = (size_t)a.H * a.W;
     if (cnt > 0) {
         for (int i = tid; i < a.plane_words; i += TC_RASTER_THREADS) plane[i] = 0;
         __syncthreads();
-        if (a.timeline && tid == 0) tl_z = clock64();
+        TC_TL(tl_z = clock64());
         const int t = a.thickness[env];
         TcPlane pl = {plane, a.H, a.W, 0, a.H};
         const int warp = tid >> 5, lane = tid & 31;
@@ -556,8 +567,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_render_classes_kernel
         TcPrim *prims = (TcPrim *)((unsigned char *)segs + tc_render_segs_bytes(a.max_edges));
         for (int base = 0; base < cnt; base += TC_SETUP_CHUNK) {
             const int nseg = min(TC_SETUP_CHUNK, cnt - base);
-            long long tc0 = 0;
-            if (a.timeline && tid == 0) tc0 = clock64();
+            TC_TL(tc0 = clock64());
             // scalar set-up of up to 16 segments: warp r takes role r (fill spans, one outline edge each, caps) of all of
             // them, lane = segment, so a warp runs one code path
             for (int i = tid; i < nseg * TC_MAX_PRIMS_PER_SEG; i += TC_RASTER_THREADS) prims[i].kind = TC_PRIM_NONE;
@@ -567,16 +577,17 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_render_classes_kernel
                 tc_polyline_setup(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, warp, prims + lane * TC_MAX_PRIMS_PER_SEG);
             }
             __syncthreads();
-            if (a.timeline && tid == 0) { long long x = clock64(); tl_setup += x - tc0; tc0 = x; }
+            TC_TL(long long x = clock64(); tl_setup += x - tc0; tc0 = x);
             // pixels: the primitives go round-robin to the warps, the pixels / rows of a primitive to the lanes
             for (int p = warp; p < nseg * TC_MAX_PRIMS_PER_SEG; p += TC_RASTER_THREADS / 32)
                 if (prims[p].kind != TC_PRIM_NONE) tc_prim_draw(g, pl, prims[p]);
             __syncthreads();
-            if (a.timeline && tid == 0) tl_draw += clock64() - tc0;
+            TC_TL(tl_draw += clock64() - tc0);
         }
     }
-    if (a.timeline && tid == 0) tl3 = clock64();
+    TC_TL(tl3 = clock64());
     tc_store_plane(out, nbytes, plane, cnt > 0);
+#ifdef TC_TIMELINE
     if (a.timeline && tid == 0) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -584,6 +595,8 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_render_classes_kernel
         r[0] = smid; r[1] = tl0; r[2] = tl1; r[3] = tl2; r[4] = tl3; r[5] = clock64();
         r[6] = cnt; r[7] = tl_z ? tl_z - tl2 : 0; r[8] = tl_setup; r[9] = tl_draw;
     }
+#endif
+#undef TC_TL
 }
 
 // ------------------------------------------------------------------------------------------------ test hook

@@ -260,8 +260,13 @@ class TinyCarloVecEnv:
                 self._refill_spawn_table_if_due()
                 cur = self._spawn_cursor.long().clamp_(max=self._K - 1)
                 nodes = torch.gather(self._spawn_table, 1, cur[:, None])[:, 0].contiguous()
-                self._spawn_cursor += mask_u8.to(torch.int32)
-                self._resets_since_refill += 1
+                if mask is None and not int(self._resets_since_refill):
+                    # a full reset right after (re)seeding consumed exactly one entry per env: top the table up now,
+                    # without reading the cursors back, so that the first refill does not land in somebody's timed loop
+                    self._upload_spawn_table(self._sampler.advance(np.ones(self.num_envs, np.int64)))
+                else:
+                    self._spawn_cursor += mask_u8.to(torch.int32)
+                    self._resets_since_refill += 1
             self._spawn_nodes = nodes
             if self.autoreset:
                 self.done_flags.masked_fill_(mask_u8.bool(), 0)
@@ -340,6 +345,30 @@ class TinyCarloVecEnv:
             si = torch.empty((self.num_envs, _lib.TC_SI_N), dtype=torch.int32, device=self.device)
             _lib.check(self._L.tc_get_state(self._h, _ptr(sf), _ptr(si), self._stream()), "tc_get_state")
         return {"sf": sf, "si": si}
+
+    def checkpoint(self) -> Dict[str, Any]:
+        """Everything needed to resume a rollout bit for bit: car state, the spawn streams (per-env PCG64 states, the
+        pre-drawn table and its cursors) and the autoreset flags. The reference has no counterpart."""
+        ck = {k: v.cpu() for k, v in self.state_dict().items()}
+        if self._seeded:
+            ck["spawn_cursor"] = self._spawn_cursor.cpu()
+            ck["spawn_sampler"] = self._sampler.state_dict()
+            ck["resets_since_refill"] = self._resets_since_refill
+        if self.autoreset and hasattr(self, "done_flags"):
+            ck["done_flags"] = self.done_flags.cpu()
+        return ck
+
+    def restore(self, ck: Dict[str, Any]):
+        self.load_state_dict({"sf": ck["sf"], "si": ck["si"]})
+        if "spawn_sampler" in ck:
+            self._sampler.load_state_dict(ck["spawn_sampler"])
+            self._seeded = True
+            self._upload_spawn_table(self._sampler.table)
+            self._spawn_cursor.copy_(ck["spawn_cursor"])
+            self._resets_since_refill = int(ck["resets_since_refill"])
+        if "done_flags" in ck and self.autoreset:
+            self.done_flags.copy_(ck["done_flags"])
+        self.render_obs()
 
     def load_state_dict(self, state: Dict[str, torch.Tensor]):
         with torch.cuda.device(self.device):

@@ -2,9 +2,15 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import subprocess
 import numpy as np, torch, ctypes as C
 from pair_util import make_config
-from tinycarlo_b200 import TinyCarloVecEnv, _lib
+from tinycarlo_b200 import _lib
+# the timeline counters are compiled in only with -DTC_TIMELINE: build that variant next to the product library
+VARIANT = os.path.join(_lib.LIB_DIR, "variant_timeline.so")
+subprocess.check_call(["nvcc"] + _lib.NVCC_FLAGS + ["-DTC_TIMELINE", "-o", VARIANT, os.path.join(_lib.CSRC, "tc_api.cu")])
+_lib.LIB_PATH = VARIANT
+from tinycarlo_b200 import TinyCarloVecEnv
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 cfg = make_config("knuffingen", "classes", cam={"resolution": [480, 640]})
