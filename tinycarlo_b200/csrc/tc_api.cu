@@ -56,6 +56,11 @@ struct TcHandle {
     int stagger_ns = 0, n_sms = 148;
     long long *timeline = nullptr;
     bool fused_ok = false;
+    int render_threads = 256;
+    // fused kernel geometry: per class (large frames) or all classes per block (small frames)
+    int fused_all = 0, fused_nodes = 0, fused_edges = 0, fused_cblob = 0, fused_words = 0;
+    TcClassBlob all_desc{};
+    int32_t edge_off_h[TC_MAX_CLASSES + 1] = {0};
     uint8_t *ar_done = nullptr; // autoreset: caller-owned device buffers
     const int32_t *ar_table = nullptr;
     int32_t *ar_cursor = nullptr;
@@ -172,6 +177,8 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     TC_TRYH(tc_dev_alloc(h, &h->d_cblob_desc, (size_t)C));
     TC_CUDAH(cudaMemcpy(h->d_cblob_desc, pk.cblob_desc.data(), sizeof(TcClassBlob) * C, cudaMemcpyHostToDevice));
     h->max_cblob_bytes = pk.max_cblob_bytes;
+    h->all_desc = pk.all_desc;
+    for (int c = 0; c <= C; c++) h->edge_off_h[c] = map->ll_edge_off[c];
     TC_TRYH(tc_dev_alloc(h, &h->d_edge_off, (size_t)C + 1));
     TC_CUDAH(cudaMemcpy(h->d_edge_off, map->ll_edge_off, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice));
 
@@ -211,11 +218,26 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
         if (sg) h->stagger_ns = atoi(sg);
     }
     h->plane_words_full = (int)(((size_t)h->H * h->W + 31) / 32) + 1;
-    h->render_smem = tc_render_smem_bytes(h->max_nodes, h->max_edges, h->max_cblob_bytes, h->plane_words_full);
-    h->fused_ok = h->render_smem <= 56 * 1024; // >= 4 blocks per SM; larger frames take the banded two-kernel path
+    {
+        // one block per (env, class) with a full-frame plane, or - when all C planes, the union graph and its scratch fit
+        // comfortably (small frames) - one block per env rendering all classes: 1/C of the blocks, barriers and table loads
+        const int words_all = (int)(((size_t)C * h->H * h->W + 31) / 32) + 1;
+        const size_t smem_all = tc_render_smem_bytes(sumN, sumE, pk.all_desc.bytes, words_all);
+        const size_t smem_one = tc_render_smem_bytes(h->max_nodes, h->max_edges, h->max_cblob_bytes, h->plane_words_full);
+        bool all = smem_all <= 100 * 1024 && (size_t)C * h->H * h->W <= 128 * 1024;
+        if (const char *fa = getenv("TC_FUSED_ALL")) all = atoi(fa) != 0 && smem_all <= 200 * 1024;
+        h->fused_all = all ? 1 : 0;
+        h->fused_nodes = all ? sumN : h->max_nodes; h->fused_edges = all ? sumE : h->max_edges;
+        h->fused_cblob = all ? pk.all_desc.bytes : h->max_cblob_bytes; h->fused_words = all ? words_all : h->plane_words_full;
+        h->render_smem = all ? smem_all : smem_one;
+        h->fused_ok = all || smem_one <= 56 * 1024; // >= 4 blocks per SM; larger frames take the banded two-kernel path
+    }
     if (h->fused_ok) {
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (const char *rt = getenv("TC_RENDER_THREADS")) h->render_threads = atoi(rt) == 128 ? 128 : 256;
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -264,13 +286,17 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
     const int N = h->n_envs, C = h->C;
     if (obs && obs_format == TC_OBS_CLASSES && h->fused_ok && !seg_count_out && !seg_out) {
         TcRenderArgs fa;
-        fa.cblob_desc = h->d_cblob_desc; fa.cblob = h->d_cblob; fa.max_cblob_bytes = h->max_cblob_bytes; fa.n_envs = N; fa.n_classes = C; fa.max_nodes = h->max_nodes; fa.max_edges = h->max_edges;
-        fa.H = h->H; fa.W = h->W; fa.plane_words = h->plane_words_full; fa.pose = h->d_pose; fa.cam = h->d_cam; fa.thickness = h->d_thick;
+        fa.cblob_desc = h->d_cblob_desc; fa.cblob = h->d_cblob; fa.max_cblob_bytes = h->fused_cblob; fa.n_envs = N; fa.n_classes = C;
+        fa.max_nodes = h->fused_nodes; fa.max_edges = h->fused_edges;
+        fa.H = h->H; fa.W = h->W; fa.plane_words = h->fused_words; fa.all_classes = h->fused_all; fa.all_desc = h->all_desc;
+        memcpy(fa.edge_off, h->edge_off_h, sizeof(fa.edge_off)); fa.pose = h->d_pose; fa.cam = h->d_cam; fa.thickness = h->d_thick;
         fa.mask = mask; fa.obs = obs;
         fa.stagger_ns = mask ? 0 : h->stagger_ns; fa.n_sms = h->n_sms;
         fa.timeline = mask ? nullptr : h->timeline;
         if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
-        tc_render_classes_kernel<<<N * C, TC_RASTER_THREADS, h->render_smem, st>>>(fa);
+        const int grid = h->fused_all ? N : N * C;
+        if (h->render_threads == 128) tc_render_classes_kernel<128><<<grid, 128, h->render_smem, st>>>(fa);
+        else tc_render_classes_kernel<256><<<grid, 256, h->render_smem, st>>>(fa);
         h->launches++;
         TC_CUDA(cudaGetLastError());
         return TC_OK;

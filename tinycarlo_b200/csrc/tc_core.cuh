@@ -87,14 +87,17 @@ struct TcTrackTables {
     const int32_t *ll_edges;     // [sumE][2] class-local node ids
     const int32_t *ll_node_off;  // [C+1]
     const int32_t *ll_edge_off;  // [C+1]
+    const float *ll_nodes32;     // [sumN][2] float copy of ll_nodes for the pre-filter of the nearest-edge scan
+    double scan_margin;          // 2*eps of the float pre-filter (metres)
 };
 
 // Byte offsets of the sections inside the blob (all multiples of 16); filled by the host at staging.
 struct TcBlobLayout {
     int32_t n_classes, lp_n_nodes, lp_n_edges, sum_nodes, sum_edges;
     int32_t off_lp_nodes, off_lp_orient, off_lp_orient_rev, off_ll_nodes, off_lp_edges, off_next_off, off_next_edge, off_prev_off,
-        off_prev_edge, off_ll_edges, off_ll_node_off, off_ll_edge_off;
+        off_prev_edge, off_ll_edges, off_ll_node_off, off_ll_edge_off, off_ll_nodes32;
     int32_t total_bytes;
+    double scan_margin;
 };
 
 TC_HD TcTrackTables tc_track_tables(const unsigned char *base, const TcBlobLayout &L) {
@@ -114,6 +117,8 @@ TC_HD TcTrackTables tc_track_tables(const unsigned char *base, const TcBlobLayou
     t.ll_edges = (const int32_t *)(base + L.off_ll_edges);
     t.ll_node_off = (const int32_t *)(base + L.off_ll_node_off);
     t.ll_edge_off = (const int32_t *)(base + L.off_ll_edge_off);
+    t.ll_nodes32 = (const float *)(base + L.off_ll_nodes32);
+    t.scan_margin = L.scan_margin;
     return t;
 }
 
@@ -143,14 +148,22 @@ TC_HD int tc_pick_edge(const TcTrackTables &t, int node, double orientation, con
     return b + best;
 }
 
-// layer.py:126-142 on explicit node coordinates
+// layer.py:126-142 on explicit node coordinates. The reference tests |angle(p-n0) - angle(e)| <= pi/2 and
+// |angle(p-n1) - angle(-e)| <= pi/2 through four atan2 calls; the angle between two vectors is within pi/2 iff their dot
+// product is >= 0, and the two formulations can only disagree when the angle is within a few ulp of pi/2. The atan2
+// evaluation is therefore kept for the near-perpendicular band (|cos| < 1e-9, which contains the exactly perpendicular
+// cases of the reference's unit tests) and skipped everywhere else.
+TC_HD bool tc_angle_within_half_pi(double ux, double uy, double vx, double vy) {
+    double dot = ux * vx + uy * vy;
+    double scale = (fabs(ux) + fabs(uy)) * (fabs(vx) + fabs(vy));
+    if (fabs(dot) > 1e-9 * scale) return dot > 0;
+    return fabs(tc_clip_angle(atan2(uy, ux) - atan2(vy, vx))) <= TC_PI / 2;
+}
 TC_HD bool tc_within_edge_bounds(double px, double py, double n0x, double n0y, double n1x, double n1y) {
     if (px == n0x && py == n0y) return true;
     if (px == n1x && py == n1y) return true;
     double ex = n1x - n0x, ey = n1y - n0y;
-    double a0 = fabs(tc_clip_angle(atan2(py - n0y, px - n0x) - atan2(ey, ex)));
-    double a1 = fabs(tc_clip_angle(atan2(py - n1y, px - n1x) - atan2(-ey, -ex)));
-    return a0 <= TC_PI / 2 && a1 <= TC_PI / 2;
+    return tc_angle_within_half_pi(px - n0x, py - n0y, ex, ey) && tc_angle_within_half_pi(px - n1x, py - n1y, -ex, -ey);
 }
 // layer.py:144-164
 TC_HD double tc_distance_to_edge(double px, double py, double n1x, double n1y, double n2x, double n2y) {
@@ -173,6 +186,37 @@ TC_HD int tc_nearest_edge(const TcLanes &g, const double *nodes, const int32_t *
             best = e;
             bd = d;
         }
+    }
+    tc_group_argmin(g, bd, best);
+    return best;
+}
+
+// The same arg-min for the per-class laneline scans (car.py:58, the bulk of the tracking kernel's arithmetic), with a
+// float pre-filter: every edge gets a float estimate d32 of d0+d1 (|d32 - d| <= eps), the group takes the minimum, and
+// only edges with d32 <= min32 + margin (margin >= 2*eps) are evaluated in float64. The true arg-min e* satisfies
+// d32(e*) <= d(e*) + eps <= d(e) + eps <= d32(e) + 2*eps for every e, so it and all its float64 ties are candidates:
+// the result is exactly that of the full float64 scan at a fraction of the float64 square roots.
+TC_HD int tc_nearest_edge_prefiltered(const TcLanes &g, const double *nodes, const float *nodes32, const int32_t *edges, int m, double px,
+                                      double py, double margin) {
+    // single pass: min32 is the running minimum of the estimates seen by this lane; an edge is evaluated in float64
+    // when its estimate is within the margin of it. The lane's true arg-min always passes (its estimate is within 2*eps
+    // of every other estimate of the lane), so every lane ends with its exact arg-min and the group reduction is exact.
+    const float fx = (float)px, fy = (float)py, fm = (float)margin;
+    float min32 = 3.0e38f;
+    int best = -1;
+    double bd = 0;
+    for (int e = g.lane; e < m; e += g.n) {
+        int a = edges[2 * e], b = edges[2 * e + 1];
+        float ax = nodes32[2 * a] - fx, ay = nodes32[2 * a + 1] - fy, bx = nodes32[2 * b] - fx, by = nodes32[2 * b + 1] - fy;
+        float d32 = sqrtf(ax * ax + ay * ay) + sqrtf(bx * bx + by * by);
+        if (d32 <= min32 + fm) {
+            double d = fabs(tc_dist(px, py, nodes[2 * a], nodes[2 * a + 1]) + tc_dist(px, py, nodes[2 * b], nodes[2 * b + 1]));
+            if (best < 0 || d < bd) {
+                best = e;
+                bd = d;
+            }
+        }
+        min32 = d32 < min32 ? d32 : min32;
     }
     tc_group_argmin(g, bd, best);
     return best;
@@ -320,7 +364,7 @@ TC_HD TcInfo tc_get_info(const TcLanes &g, const TcTrackTables &t, const double 
             const double *nodes = t.ll_nodes + 2 * t.ll_node_off[c];
             const int32_t *edges = t.ll_edges + 2 * t.ll_edge_off[c];
             int m = t.ll_edge_off[c + 1] - t.ll_edge_off[c];
-            int e = tc_nearest_edge(g, nodes, edges, m, s.x, s.y, nullptr, 0.0, 0.0);
+            int e = tc_nearest_edge_prefiltered(g, nodes, t.ll_nodes32 + 2 * t.ll_node_off[c], edges, m, s.x, s.y, t.scan_margin);
             nearest[c] = e;
             if (e < 0) continue; // class without edges: the reference would raise on min([])
             int n0 = edges[2 * e], n1 = edges[2 * e + 1];
@@ -464,7 +508,8 @@ TC_HD bool tc_clip_pass_node(const TcClassTables &ct, const TcProjScratch &sc, c
 struct TcPlane {
     uint32_t *bits; // flat bit plane
     int H, W;
-    int y_lo, y_hi; // rows [y_lo, y_hi) of the frame live in this plane; bit index = (y-y_lo)*W + x
+    int y_lo, y_hi; // rows [y_lo, y_hi) of the frame may be drawn
+    int row_base;   // bit index = (y - row_base)*W + x: y_lo for a band plane, -c*H for class c of a stacked C*H-row plane
 };
 
 TC_HD void tc_or_word(uint32_t *p, uint32_t m) {
@@ -476,13 +521,13 @@ TC_HD void tc_or_word(uint32_t *p, uint32_t m) {
 }
 TC_HD void tc_put(const TcPlane &pl, int64_t x, int64_t y) {
     if (x < 0 || x >= pl.W || y < pl.y_lo || y >= pl.y_hi) return;
-    int64_t b = (y - pl.y_lo) * pl.W + x;
+    int64_t b = (y - pl.row_base) * pl.W + x;
     tc_or_word(pl.bits + (b >> 5), 1u << (b & 31));
 }
 // inclusive span, x already clipped to [0, W-1]
 TC_HD void tc_hline(const TcPlane &pl, int y, int x1, int x2) {
     if (y < pl.y_lo || y >= pl.y_hi || x2 < x1) return;
-    int b1 = (y - pl.y_lo) * pl.W + x1, b2 = (y - pl.y_lo) * pl.W + x2;
+    int b1 = (y - pl.row_base) * pl.W + x1, b2 = (y - pl.row_base) * pl.W + x2;
     int w1 = b1 >> 5, w2 = b2 >> 5;
     uint32_t m1 = 0xffffffffu << (b1 & 31), m2 = 0xffffffffu >> (31 - (b2 & 31));
     if (w1 == w2) tc_or_word(pl.bits + w1, m1 & m2);
@@ -718,7 +763,7 @@ TC_HD void tc_polyline_setup(int W, int H, int32_t x0, int32_t y0, int32_t x1, i
 // 32-bit pixel helpers (coordinates are frame-sized here)
 TC_HD void tc_put32(const TcPlane &pl, int x, int y) {
     if ((unsigned)x >= (unsigned)pl.W || y < pl.y_lo || y >= pl.y_hi) return;
-    int b = (y - pl.y_lo) * pl.W + x;
+    int b = (y - pl.row_base) * pl.W + x;
     tc_or_word(pl.bits + (b >> 5), 1u << (b & 31));
 }
 

@@ -120,7 +120,7 @@ HT_API void ht_render(const HtMap *m, int n, int H, int W, int fmt, int rows_per
             int y_lo = band * rows_per_band, y_hi = y_lo + rows_per_band < H ? y_lo + rows_per_band : H;
             std::vector<uint32_t> planes((size_t)C * plane_words, 0);
             for (int c = 0; c < C; c++) {
-                TcPlane pl = {planes.data() + (size_t)c * plane_words, H, W, y_lo, y_hi};
+                TcPlane pl = {planes.data() + (size_t)c * plane_words, H, W, y_lo, y_hi, y_lo};
                 const int32_t *s = seg + ((size_t)env * m->sumE + m->edge_off[c]) * 4;
                 for (int k = 0; k < seg_count[(size_t)env * C + c]; k++) tc_polyline2(g, pl, s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3], thickness[env]);
             }
@@ -147,7 +147,7 @@ HT_API void ht_polyline(uint8_t *img, int H, int W, int32_t x0, int32_t y0, int3
     if (y_hi <= 0) { y_lo = 0; y_hi = H; }
     if (nlanes == 0) nlanes = 1;
     std::vector<uint32_t> plane(((size_t)(y_hi - y_lo) * W + 31) / 32 + 1, 0);
-    TcPlane pl = {plane.data(), H, W, y_lo, y_hi};
+    TcPlane pl = {plane.data(), H, W, y_lo, y_hi, y_lo};
     if (nlanes < 0) {
         // the fused kernel's split: every role sets up its own slots (as different warps do), then 32 lanes draw
         TcPrim prims[TC_MAX_PRIMS_PER_SEG];

@@ -72,7 +72,7 @@ struct TcTrackArgs {
     TcOutputs out;
 };
 
-__global__ void __launch_bounds__(TC_TRACK_THREADS) tc_track_kernel(const TcTrackArgs a) {
+__global__ void __launch_bounds__(TC_TRACK_THREADS, 3) tc_track_kernel(const TcTrackArgs a) {
     extern __shared__ __align__(128) unsigned char smem_blob[];
     __shared__ __align__(8) uint64_t bar;
     if (threadIdx.x == 0) {
@@ -286,38 +286,39 @@ __device__ __forceinline__ uint4 tc_expand16(uint32_t b) {
 }
 
 // Stream `nbytes` bytes of 0/255 to `out` from the bit plane (bit i <-> byte i). `any` false: plane is known empty.
+template <int NT = TC_RASTER_THREADS>
 __device__ __forceinline__ void tc_store_plane(uint8_t *out, size_t nbytes, const uint32_t *plane, bool any) {
     const int tid = threadIdx.x;
     size_t head = (16 - ((uintptr_t)out & 15)) & 15;
     if (head > nbytes) head = nbytes;
-    for (size_t i = tid; i < head; i += TC_RASTER_THREADS) out[i] = (any && ((plane[i >> 5] >> (i & 31)) & 1)) ? 255 : 0;
+    for (size_t i = tid; i < head; i += NT) out[i] = (any && ((plane[i >> 5] >> (i & 31)) & 1)) ? 255 : 0;
     const size_t nvec = (nbytes - head) >> 4;
     uint4 *o4 = (uint4 *)(out + head);
     if (!any) {
         const uint4 z = make_uint4(0, 0, 0, 0);
         size_t j = tid;
-        for (; j + 3 * TC_RASTER_THREADS < nvec; j += 4 * TC_RASTER_THREADS) {
+        for (; j + 3 * NT < nvec; j += 4 * NT) {
             tc_st_cs(o4 + j, z);
-            tc_st_cs(o4 + j + TC_RASTER_THREADS, z);
-            tc_st_cs(o4 + j + 2 * TC_RASTER_THREADS, z);
-            tc_st_cs(o4 + j + 3 * TC_RASTER_THREADS, z);
+            tc_st_cs(o4 + j + NT, z);
+            tc_st_cs(o4 + j + 2 * NT, z);
+            tc_st_cs(o4 + j + 3 * NT, z);
         }
-        for (; j < nvec; j += TC_RASTER_THREADS) tc_st_cs(o4 + j, z);
+        for (; j < nvec; j += NT) tc_st_cs(o4 + j, z);
     } else {
         size_t j = tid;
-        for (; j + 3 * TC_RASTER_THREADS < nvec; j += 4 * TC_RASTER_THREADS) {
+        for (; j + 3 * NT < nvec; j += 4 * NT) {
             uint32_t b0 = tc_bits16(plane, (uint32_t)(head + 16 * j));
-            uint32_t b1 = tc_bits16(plane, (uint32_t)(head + 16 * (j + TC_RASTER_THREADS)));
-            uint32_t b2 = tc_bits16(plane, (uint32_t)(head + 16 * (j + 2 * TC_RASTER_THREADS)));
-            uint32_t b3 = tc_bits16(plane, (uint32_t)(head + 16 * (j + 3 * TC_RASTER_THREADS)));
+            uint32_t b1 = tc_bits16(plane, (uint32_t)(head + 16 * (j + NT)));
+            uint32_t b2 = tc_bits16(plane, (uint32_t)(head + 16 * (j + 2 * NT)));
+            uint32_t b3 = tc_bits16(plane, (uint32_t)(head + 16 * (j + 3 * NT)));
             tc_st_cs(o4 + j, tc_expand16(b0));
-            tc_st_cs(o4 + j + TC_RASTER_THREADS, tc_expand16(b1));
-            tc_st_cs(o4 + j + 2 * TC_RASTER_THREADS, tc_expand16(b2));
-            tc_st_cs(o4 + j + 3 * TC_RASTER_THREADS, tc_expand16(b3));
+            tc_st_cs(o4 + j + NT, tc_expand16(b1));
+            tc_st_cs(o4 + j + 2 * NT, tc_expand16(b2));
+            tc_st_cs(o4 + j + 3 * NT, tc_expand16(b3));
         }
-        for (; j < nvec; j += TC_RASTER_THREADS) tc_st_cs(o4 + j, tc_expand16(tc_bits16(plane, (uint32_t)(head + 16 * j))));
+        for (; j < nvec; j += NT) tc_st_cs(o4 + j, tc_expand16(tc_bits16(plane, (uint32_t)(head + 16 * j))));
     }
-    for (size_t i = head + (nvec << 4) + tid; i < nbytes; i += TC_RASTER_THREADS)
+    for (size_t i = head + (nvec << 4) + tid; i < nbytes; i += NT)
         out[i] = (any && ((plane[i >> 5] >> (i & 31)) & 1)) ? 255 : 0;
 }
 
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_classes_kernel(co
         __syncthreads();
         const int32_t *seg = a.seg + ((size_t)env * a.sum_edges + a.edge_off[c]) * 4;
         const int t = a.thickness[env];
-        TcPlane pl = {plane, a.H, a.W, y_lo, y_hi};
+        TcPlane pl = {plane, a.H, a.W, y_lo, y_hi, y_lo};
         TcLanes g = {(int)(threadIdx.x & 31), 32};
         for (int k = threadIdx.x >> 5; k < cnt; k += TC_RASTER_THREADS / 32) {
             int4 s4 = *(const int4 *)(seg + 4 * k);
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const 
         for (int c = 0; c < C; c++) {
             const int cnt = a.seg_count[(size_t)env * C + c];
             const int32_t *seg = a.seg + ((size_t)env * a.sum_edges + a.edge_off[c]) * 4;
-            TcPlane pl = {planes + (size_t)c * a.plane_words, a.H, a.W, y_lo, y_hi};
+            TcPlane pl = {planes + (size_t)c * a.plane_words, a.H, a.W, y_lo, y_hi, y_lo};
             // warps take segments round-robin across all classes
             for (int k = 0; k < cnt; k++, k0++)
                 if ((k0 & (TC_RASTER_THREADS / 32 - 1)) == (int)(threadIdx.x >> 5)) {
@@ -438,6 +439,9 @@ struct TcRenderArgs {
     const int32_t *thickness;  // [N]
     const uint8_t *mask;       // optional
     uint8_t *obs;              // [N,C,H,W]
+    int all_classes;           // 1: a block renders all C classes of an env (stacked C*H-row plane), 0: one class
+    TcClassBlob all_desc;      // the union graph of all classes (all_classes == 1)
+    int32_t edge_off[TC_MAX_CLASSES + 1];
     int stagger_ns, n_sms;     // first-wave phase stagger (see the kernel)
     long long *timeline;       // optional debug [N*C][10]: smid, clock at start / tables landed / geometry done / raster done / end
 };
@@ -452,18 +456,18 @@ __host__ __device__ inline size_t tc_render_union_bytes(int max_nodes, int max_c
 __host__ __device__ inline size_t tc_render_segs_bytes(int max_edges) { return (size_t)(max_edges > 0 ? max_edges : 1) * 16; }
 __host__ __device__ inline size_t tc_render_smem_bytes(int max_nodes, int max_edges, int max_cblob_bytes, int plane_words) {
     return tc_render_union_bytes(max_nodes, max_cblob_bytes, plane_words) + tc_render_segs_bytes(max_edges) +
-           (size_t)TC_SETUP_CHUNK * TC_MAX_PRIMS_PER_SEG * sizeof(TcPrim);
+           (size_t)TC_SETUP_CHUNK * TC_MAX_PRIMS_PER_SEG * sizeof(TcPrim) + (size_t)((max_edges + 15) & ~15);
 }
 
-#ifndef TC_RENDER_MIN_BLOCKS
-#define TC_RENDER_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(TC_RASTER_THREADS, TC_RENDER_MIN_BLOCKS) tc_render_classes_kernel(const TcRenderArgs a) {
+// NT threads per block: 256 for large frames (4 blocks/SM, stores dominate), 128 for small ones (8 blocks/SM: the block's
+// work is then the latency-bound camera pass, and twice as many independent blocks hide it better)
+template <int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const TcRenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int seg_cnt;
     __shared__ __align__(8) uint64_t bar;
     __shared__ double s_pose[12], s_cam[TC_CAM_N];
-    const int env = blockIdx.x / a.n_classes, c = blockIdx.x % a.n_classes;
+    const int env = a.all_classes ? blockIdx.x : blockIdx.x / a.n_classes, c = a.all_classes ? 0 : blockIdx.x % a.n_classes;
     if (a.mask && !a.mask[env]) return;
     const int tid = threadIdx.x;
     // Every block does a latency-bound geometry phase and then a bandwidth-bound store phase. Blocks that share an SM
@@ -491,7 +495,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, TC_RENDER_MIN_BLOCKS) tc_re
 #define TC_TL(stmt) do { } while (0)
 #endif
     TC_TL(tl0 = clock64());
-    const TcClassBlob cb = a.cblob_desc[c];
+    const TcClassBlob cb = a.all_classes ? a.all_desc : a.cblob_desc[c];
     unsigned char *tab_smem = smem_raw + tc_render_scratch_bytes(a.max_nodes);
     if (tid == 0) {
         seg_cnt = 0;
@@ -502,6 +506,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, TC_RENDER_MIN_BLOCKS) tc_re
     }
     const int n = cb.n_nodes, m = cb.n_edges;
     int4 *segs = (int4 *)(smem_raw + tc_render_union_bytes(a.max_nodes, a.max_cblob_bytes, a.plane_words));
+    uint8_t *seg_cls = (uint8_t *)segs + tc_render_segs_bytes(a.max_edges) + (size_t)TC_SETUP_CHUNK * TC_MAX_PRIMS_PER_SEG * sizeof(TcPrim);
     uint32_t *plane = (uint32_t *)smem_raw;
     {
         const size_t np = (size_t)((a.max_nodes + 15) & ~15);
@@ -520,24 +525,24 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, TC_RENDER_MIN_BLOCKS) tc_re
         tc_mbar_wait(&bar, 0); // the class's tables have landed in shared memory
         TC_TL(tl1 = clock64());
         const TcClassTables ct = tc_class_tables_from_blob(tab_smem, cb);
-        for (int v = tid; v < n; v += TC_RASTER_THREADS) {
+        for (int v = tid; v < n; v += NT) {
             double X, Y, Z;
             tc_transform_node(pose, ct.nodes[2 * v], ct.nodes[2 * v + 1], X, Y, Z);
             sc.Px[v] = X; sc.Py[v] = Y; sc.Pz[v] = Z;
             fA[v] = Z < 0;
         }
         __syncthreads();
-        for (int v = tid; v < n; v += TC_RASTER_THREADS) fB[v] = fA[v] | (uint8_t)tc_clip_pass_node(ct, sc, fA, v, true, -0.0000001);
+        for (int v = tid; v < n; v += NT) fB[v] = fA[v] | (uint8_t)tc_clip_pass_node(ct, sc, fA, v, true, -0.0000001);
         __syncthreads();
-        for (int v = tid; v < n; v += TC_RASTER_THREADS) fA[v] = fB[v] | (uint8_t)tc_clip_pass_node(ct, sc, fB, v, false, -0.0000001);
+        for (int v = tid; v < n; v += NT) fA[v] = fB[v] | (uint8_t)tc_clip_pass_node(ct, sc, fB, v, false, -0.0000001);
         __syncthreads();
-        for (int v = tid; v < n; v += TC_RASTER_THREADS) rA[v] = sc.Pz[v] > -max_range;
+        for (int v = tid; v < n; v += NT) rA[v] = sc.Pz[v] > -max_range;
         __syncthreads();
-        for (int v = tid; v < n; v += TC_RASTER_THREADS) rB[v] = rA[v] | (uint8_t)tc_clip_pass_node(ct, sc, rA, v, true, -max_range);
+        for (int v = tid; v < n; v += NT) rB[v] = rA[v] | (uint8_t)tc_clip_pass_node(ct, sc, rA, v, true, -max_range);
         __syncthreads();
-        for (int v = tid; v < n; v += TC_RASTER_THREADS) rA[v] = rB[v] | (uint8_t)tc_clip_pass_node(ct, sc, rB, v, false, -max_range);
+        for (int v = tid; v < n; v += NT) rA[v] = rB[v] | (uint8_t)tc_clip_pass_node(ct, sc, rB, v, false, -max_range);
         __syncthreads();
-        for (int v = tid; v < n; v += TC_RASTER_THREADS) {
+        for (int v = tid; v < n; v += NT) {
             double u, w;
             tc_project(cam, sc.Px[v], sc.Py[v], sc.Pz[v], u, w);
             sc.ix[v] = tc_np_int32(u);
@@ -546,22 +551,30 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, TC_RENDER_MIN_BLOCKS) tc_re
         }
         __syncthreads();
         // kept edges (camera.py:95); order is irrelevant for a single-colour plane
-        for (int e = tid; e < m; e += TC_RASTER_THREADS) {
+        for (int e = tid; e < m; e += NT) {
             int n0 = ct.edges[2 * e], n1 = ct.edges[2 * e + 1];
-            if (sc.vis[n0] || sc.vis[n1]) segs[atomicAdd(&seg_cnt, 1)] = make_int4(sc.ix[n0], sc.iy[n0], sc.ix[n1], sc.iy[n1]);
+            if (sc.vis[n0] || sc.vis[n1]) {
+                int slot = atomicAdd(&seg_cnt, 1);
+                segs[slot] = make_int4(sc.ix[n0], sc.iy[n0], sc.ix[n1], sc.iy[n1]);
+                if (a.all_classes) {   // class of the edge = plane it is drawn into
+                    int cls = 0;
+                    while (cls + 1 < a.n_classes && e >= a.edge_off[cls + 1]) cls++;
+                    seg_cls[slot] = (uint8_t)cls;
+                }
+            }
         }
         __syncthreads(); // scratch and tables are dead from here on; the plane takes their place
     }
     const int cnt = seg_cnt;
     TC_TL(tl2 = clock64());
+    const int n_planes = a.all_classes ? a.n_classes : 1;
     uint8_t *out = a.obs + ((size_t)env * a.n_classes + c) * a.H * a.W;
-    const size_t nbytes = (size_t)a.H * a.W;
+    const size_t nbytes = (size_t)n_planes * a.H * a.W;
     if (cnt > 0) {
-        for (int i = tid; i < a.plane_words; i += TC_RASTER_THREADS) plane[i] = 0;
+        for (int i = tid; i < a.plane_words; i += NT) plane[i] = 0;
         __syncthreads();
         TC_TL(tl_z = clock64());
         const int t = a.thickness[env];
-        TcPlane pl = {plane, a.H, a.W, 0, a.H};
         const int warp = tid >> 5, lane = tid & 31;
         TcLanes g = {lane, 32};
         TcPrim *prims = (TcPrim *)((unsigned char *)segs + tc_render_segs_bytes(a.max_edges));
@@ -570,23 +583,28 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS, TC_RENDER_MIN_BLOCKS) tc_re
             TC_TL(tc0 = clock64());
             // scalar set-up of up to 16 segments: warp r takes role r (fill spans, one outline edge each, caps) of all of
             // them, lane = segment, so a warp runs one code path
-            for (int i = tid; i < nseg * TC_MAX_PRIMS_PER_SEG; i += TC_RASTER_THREADS) prims[i].kind = TC_PRIM_NONE;
+            for (int i = tid; i < nseg * TC_MAX_PRIMS_PER_SEG; i += NT) prims[i].kind = TC_PRIM_NONE;
             __syncthreads();
-            if (warp < TC_N_ROLES && lane < nseg) {
+            if (lane < nseg) {
                 int4 s4 = segs[base + lane];
-                tc_polyline_setup(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, warp, prims + lane * TC_MAX_PRIMS_PER_SEG);
+                for (int role = warp; role < TC_N_ROLES; role += NT / 32)
+                    tc_polyline_setup(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, role, prims + lane * TC_MAX_PRIMS_PER_SEG);
             }
             __syncthreads();
             TC_TL(long long x = clock64(); tl_setup += x - tc0; tc0 = x);
             // pixels: the primitives go round-robin to the warps, the pixels / rows of a primitive to the lanes
-            for (int p = warp; p < nseg * TC_MAX_PRIMS_PER_SEG; p += TC_RASTER_THREADS / 32)
-                if (prims[p].kind != TC_PRIM_NONE) tc_prim_draw(g, pl, prims[p]);
+            for (int p = warp; p < nseg * TC_MAX_PRIMS_PER_SEG; p += (NT / 32))
+                if (prims[p].kind != TC_PRIM_NONE) {
+                    const int cls = a.all_classes ? seg_cls[base + p / TC_MAX_PRIMS_PER_SEG] : 0;
+                    TcPlane pl = {plane, a.H, a.W, 0, a.H, -cls * a.H};
+                    tc_prim_draw(g, pl, prims[p]);
+                }
             __syncthreads();
             TC_TL(tl_draw += clock64() - tc0);
         }
     }
     TC_TL(tl3 = clock64());
-    tc_store_plane(out, nbytes, plane, cnt > 0);
+    tc_store_plane<NT>(out, nbytes, plane, cnt > 0);
 #ifdef TC_TIMELINE
     if (a.timeline && tid == 0) {
         unsigned smid;
