@@ -208,7 +208,7 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     h->proj_smem = tc_proj_smem_bytes(h->max_nodes);
     const size_t plane_budget = 48 * 1024;
     tc_band_geometry(h->H, h->W, 1, plane_budget, &h->rows_per_band_cls, &h->n_bands_cls, &h->plane_words_cls);
-    tc_band_geometry(h->H, h->W, C + 1, 2 * plane_budget, &h->rows_per_band_rgb, &h->n_bands_rgb, &h->plane_words_rgb);
+    tc_band_geometry(h->H, h->W, C, plane_budget, &h->rows_per_band_rgb, &h->n_bands_rgb, &h->plane_words_rgb);
     for (int c = 0; c < C; c++) h->max_edges = std::max(h->max_edges, map->ll_edge_off[c + 1] - map->ll_edge_off[c]);
     {
         cudaDeviceProp prop;
@@ -234,10 +234,12 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     }
     if (h->fused_ok) {
         if (const char *rt = getenv("TC_RENDER_THREADS")) h->render_threads = atoi(rt) == 128 ? 128 : 256;
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -246,7 +248,7 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     TC_CUDAH(cudaFuncSetAttribute(tc_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->proj_smem));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->plane_words_cls * 4)));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_rgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)((size_t)h->plane_words_rgb * 4 * (C + 1))));
+                                  (int)tc_raster_rgb_smem_bytes(C, h->plane_words_rgb)));
     *out = h;
     return TC_OK;
 }
@@ -284,19 +286,22 @@ int tc_set_wrapped(TcHandle *h, int32_t wrapped) {
 static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int obs_format, int32_t *seg_count_out, int32_t *seg_out,
                             cudaStream_t st, cudaEvent_t after_project = nullptr) {
     const int N = h->n_envs, C = h->C;
-    if (obs && obs_format == TC_OBS_CLASSES && h->fused_ok && !seg_count_out && !seg_out) {
+    if (obs && h->fused_ok && !seg_count_out && !seg_out && (obs_format == TC_OBS_CLASSES || h->fused_all)) {
         TcRenderArgs fa;
         fa.cblob_desc = h->d_cblob_desc; fa.cblob = h->d_cblob; fa.max_cblob_bytes = h->fused_cblob; fa.n_envs = N; fa.n_classes = C;
         fa.max_nodes = h->fused_nodes; fa.max_edges = h->fused_edges;
         fa.H = h->H; fa.W = h->W; fa.plane_words = h->fused_words; fa.all_classes = h->fused_all; fa.all_desc = h->all_desc;
-        memcpy(fa.edge_off, h->edge_off_h, sizeof(fa.edge_off)); fa.pose = h->d_pose; fa.cam = h->d_cam; fa.thickness = h->d_thick;
+        memcpy(fa.edge_off, h->edge_off_h, sizeof(fa.edge_off));
+        fa.rgb = obs_format == TC_OBS_RGB ? 1 : 0;
+        memcpy(fa.colors, h->colors, sizeof(fa.colors)); fa.pose = h->d_pose; fa.cam = h->d_cam; fa.thickness = h->d_thick;
         fa.mask = mask; fa.obs = obs;
         fa.stagger_ns = mask ? 0 : h->stagger_ns; fa.n_sms = h->n_sms;
         fa.timeline = mask ? nullptr : h->timeline;
         if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
         const int grid = h->fused_all ? N : N * C;
-        if (h->render_threads == 128) tc_render_classes_kernel<128><<<grid, 128, h->render_smem, st>>>(fa);
-        else tc_render_classes_kernel<256><<<grid, 256, h->render_smem, st>>>(fa);
+        if (fa.rgb) tc_render_classes_kernel<256, true><<<grid, 256, h->render_smem, st>>>(fa);
+        else if (h->render_threads == 128) tc_render_classes_kernel<128, false><<<grid, 128, h->render_smem, st>>>(fa);
+        else tc_render_classes_kernel<256, false><<<grid, 256, h->render_smem, st>>>(fa);
         h->launches++;
         TC_CUDA(cudaGetLastError());
         return TC_OK;
@@ -320,7 +325,7 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
         tc_raster_classes_kernel<<<N * C * ra.n_bands, TC_RASTER_THREADS, (size_t)ra.plane_words * 4, st>>>(ra);
     } else {
         ra.rows_per_band = h->rows_per_band_rgb; ra.n_bands = h->n_bands_rgb; ra.plane_words = h->plane_words_rgb;
-        tc_raster_rgb_kernel<<<N * ra.n_bands, TC_RASTER_THREADS, (size_t)ra.plane_words * 4 * (C + 1), st>>>(ra);
+        tc_raster_rgb_kernel<<<N * ra.n_bands, TC_RASTER_THREADS, tc_raster_rgb_smem_bytes(C, ra.plane_words), st>>>(ra);
     }
     h->launches++;
     TC_CUDA(cudaGetLastError());

@@ -16,6 +16,7 @@
 #define TC_TRACK_THREADS 256
 #define TC_PROJ_THREADS 128
 #define TC_RASTER_THREADS 256
+#define TC_SETUP_CHUNK 16 // segments set up per round (one thread per segment and role), then drawn by all warps
 
 // ------------------------------------------------------------------------------------------------ TMA / mbarrier PTX
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -322,6 +323,75 @@ __device__ __forceinline__ void tc_store_plane(uint8_t *out, size_t nbytes, cons
         out[i] = (any && ((plane[i >> 5] >> (i & 31)) & 1)) ? 255 : 0;
 }
 
+// RGB composition from C class planes (class c starts at bit c*stride_bits of `planes`; a pad word follows the last
+// plane): byte q of the [rows,W,3] image belongs to pixel q/3, channel q%3, and takes the colour of the LAST class drawn
+// there (painter's order, renderer.py:41-43). 16 output bytes touch at most 6 pixels: one funnel-shifted 6-bit window per
+// class gives the winning colour of each of them; the 16 bytes are then cut out of that 18-byte pixel stream.
+template <int R>
+__device__ __forceinline__ uint4 tc_rgb_cut16(const uint32_t (&col)[6]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = R + 4 * m + k; // byte i of the stream: pixel i/3, channel i%3
+            v |= ((col[i / 3] >> (8 * (i % 3))) & 0xffu) << (8 * k);
+        }
+        w[m] = v;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int NT>
+__device__ __forceinline__ void tc_store_rgb(uint8_t *out, uint32_t npx, const uint32_t *planes, uint32_t stride_bits, int C,
+                                             const uint32_t *color24 /* shared: r | g<<8 | b<<16 per class */, bool any,
+                                             const uint32_t *any_plane = nullptr /* optional OR of the class planes */) {
+    const int tid = threadIdx.x;
+    const uint32_t nbytes = npx * 3u;
+    auto byte_at = [&](uint32_t q) -> uint8_t {   // scalar path for the unaligned head / tail
+        if (!any) return 0;
+        uint32_t p = q / 3u;
+        uint32_t v = 0;
+        for (int c = 0; c < C; c++) {
+            uint32_t bi = (uint32_t)c * stride_bits + p;
+            if ((planes[bi >> 5] >> (bi & 31)) & 1) v = color24[c];
+        }
+        return (uint8_t)(v >> (8 * (q - 3u * p)));
+    };
+    uint32_t head = (16u - (uint32_t)((uintptr_t)out & 15)) & 15u;
+    if (head > nbytes) head = nbytes;
+    for (uint32_t i = tid; i < head; i += NT) out[i] = byte_at(i);
+    const uint32_t nvec = (nbytes - head) >> 4;
+    uint4 *o4 = (uint4 *)(out + head);
+    for (uint32_t j = tid; j < nvec; j += NT) {
+        uint32_t q0 = head + 16u * j;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (any) {
+            const uint32_t p0 = q0 / 3u;
+            uint32_t col[6] = {0, 0, 0, 0, 0, 0};
+            uint32_t bits = 0;
+            const bool look = !any_plane || (__funnelshift_r(any_plane[p0 >> 5], any_plane[(p0 >> 5) + 1], p0 & 31) & 0x3fu);
+            if (look) for (int c = 0; c < C; c++) {
+                uint32_t bi = (uint32_t)c * stride_bits + p0;
+                uint32_t w = __funnelshift_r(planes[bi >> 5], planes[(bi >> 5) + 1], bi & 31) & 0x3fu;
+                if (w) {
+                    const uint32_t cc = color24[c];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) col[k] = ((w >> k) & 1u) ? cc : col[k];
+                    bits |= w;
+                }
+            }
+            if (bits) {
+                const uint32_t r = q0 - 3u * p0;
+                v = r == 0 ? tc_rgb_cut16<0>(col) : (r == 1 ? tc_rgb_cut16<1>(col) : tc_rgb_cut16<2>(col));
+            }
+        }
+        tc_st_cs(o4 + j, v);
+    }
+    for (uint32_t i = head + (nvec << 4) + tid; i < nbytes; i += NT) out[i] = byte_at(i);
+}
+
 // classes: grid = N*C*n_bands blocks; each owns rows [y_lo, y_hi) of one class plane
 __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_classes_kernel(const TcRasterArgs a) {
     extern __shared__ __align__(16) uint32_t plane[];
@@ -350,79 +420,76 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_classes_kernel(co
     tc_store_plane(out, nbytes, plane, cnt > 0);
 }
 
-// rgb: grid = N*n_bands blocks; C class planes + an "any" plane; later classes overwrite earlier ones (renderer.py:41-43)
+// rgb, large frames: grid = N*n_bands blocks; C class planes of the band; later classes overwrite earlier ones
+// (renderer.py:41-43). Segments come from tc_project_kernel; set-up is split by role over the warps like in the fused kernel.
+__host__ __device__ inline size_t tc_raster_rgb_smem_bytes(int C, int plane_words) {
+    return ((((size_t)C * plane_words + 1) * 4 + 15) & ~(size_t)15) + (size_t)TC_SETUP_CHUNK * TC_MAX_PRIMS_PER_SEG * sizeof(TcPrim);
+}
 __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const TcRasterArgs a) {
     extern __shared__ __align__(16) uint32_t planes[];
+    __shared__ int list_src[TC_RASTER_THREADS], list_c[TC_RASTER_THREADS], list_n;
+    __shared__ uint32_t color24[TC_MAX_CLASSES];
+    __shared__ int cls_cnt[TC_MAX_CLASSES];
+    const int C = a.n_classes;
     const int band = blockIdx.x % a.n_bands;
     const int env = blockIdx.x / a.n_bands;
     if (a.mask && !a.mask[env]) return;
-    const int C = a.n_classes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < TC_MAX_CLASSES) {
+        color24[tid] = a.colors[3 * tid] | (a.colors[3 * tid + 1] << 8) | (a.colors[3 * tid + 2] << 16);
+        cls_cnt[tid] = tid < C ? a.seg_count[(size_t)env * C + tid] : 0;
+    }
+    __syncthreads();
     const int y_lo = band * a.rows_per_band;
     const int y_hi = min(a.H, y_lo + a.rows_per_band);
     uint8_t *out = a.obs + ((size_t)env * a.H + y_lo) * a.W * 3;
-    const size_t nbytes = (size_t)(y_hi - y_lo) * a.W * 3;
     int total = 0;
-    for (int c = 0; c < C; c++) total += a.seg_count[(size_t)env * C + c];
-    uint32_t *anyp = planes + (size_t)C * a.plane_words;
+    for (int c = 0; c < C; c++) total += cls_cnt[c];
+    bool drew = false;
     if (total > 0) {
-        for (int i = threadIdx.x; i < (C + 1) * a.plane_words; i += TC_RASTER_THREADS) planes[i] = 0;
-        __syncthreads();
+        for (int i = tid; i < C * a.plane_words + 1; i += TC_RASTER_THREADS) planes[i] = 0;
         const int t = a.thickness[env];
-        TcLanes g = {(int)(threadIdx.x & 31), 32};
-        int k0 = 0;
-        for (int c = 0; c < C; c++) {
-            const int cnt = a.seg_count[(size_t)env * C + c];
-            const int32_t *seg = a.seg + ((size_t)env * a.sum_edges + a.edge_off[c]) * 4;
-            TcPlane pl = {planes + (size_t)c * a.plane_words, a.H, a.W, y_lo, y_hi, y_lo};
-            // warps take segments round-robin across all classes
-            for (int k = 0; k < cnt; k++, k0++)
-                if ((k0 & (TC_RASTER_THREADS / 32 - 1)) == (int)(threadIdx.x >> 5)) {
-                    int4 s4 = *(const int4 *)(seg + 4 * k);
-                    tc_polyline2(g, pl, s4.x, s4.y, s4.z, s4.w, t);
+        TcLanes g = {lane, 32};
+        TcPrim *prims = (TcPrim *)((unsigned char *)planes + ((((size_t)C * a.plane_words + 1) * 4 + 15) & ~(size_t)15));
+        for (int win = 0; win < total; win += TC_RASTER_THREADS) {
+            // segments of this window that can touch the band's rows (all primitives stay within t+2 rows of the end points)
+            if (tid == 0) list_n = 0;
+            __syncthreads();
+            if (win + tid < total) {
+                int k = win + tid, c = 0;
+                while (k >= cls_cnt[c]) { k -= cls_cnt[c]; c++; }
+                const int src = a.edge_off[c] + k;
+                int4 s4 = *(const int4 *)(a.seg + ((size_t)env * a.sum_edges + src) * 4);
+                const long long lo = (long long)min(s4.y, s4.w) - t - 2, hi = (long long)max(s4.y, s4.w) + t + 2;
+                if (hi >= y_lo && lo < y_hi) {
+                    int slot = atomicAdd(&list_n, 1);
+                    list_src[slot] = src;
+                    list_c[slot] = c;
                 }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < a.plane_words; i += TC_RASTER_THREADS) {
-            uint32_t o = 0;
-            for (int c = 0; c < C; c++) o |= planes[(size_t)c * a.plane_words + i];
-            anyp[i] = o;
-        }
-        __syncthreads();
-    }
-    // byte stream: byte q belongs to pixel q/3, channel q%3
-    size_t head = (16 - ((uintptr_t)out & 15)) & 15;
-    if (head > nbytes) head = nbytes;
-    auto byte_at = [&](size_t q) -> uint8_t {
-        if (total == 0) return 0;
-        size_t p = q / 3;
-        int ch = (int)(q - 3 * p);
-        uint8_t v = 0;
-        for (int c = 0; c < C; c++)
-            if ((planes[(size_t)c * a.plane_words + (p >> 5)] >> (p & 31)) & 1) v = a.colors[3 * c + ch];
-        return v;
-    };
-    for (size_t i = threadIdx.x; i < head; i += TC_RASTER_THREADS) out[i] = byte_at(i);
-    const size_t nvec = (nbytes - head) >> 4;
-    uint4 *o4 = (uint4 *)(out + head);
-    for (size_t j = threadIdx.x; j < nvec; j += TC_RASTER_THREADS) {
-        size_t q0 = head + 16 * j;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (total > 0) {
-            // pixels q0/3 .. (q0+15)/3: at most 6 pixels -> 6 bits of the "any" plane
-            uint32_t p0 = (uint32_t)(q0 / 3);
-            uint32_t w = p0 >> 5;
-            uint32_t bits = __funnelshift_r(anyp[w], anyp[w + 1], p0 & 31) & 0x3fu;
-            if (bits) {
-                uint32_t r[4] = {0, 0, 0, 0};
-                for (int k = 0; k < 16; k++) r[k >> 2] |= (uint32_t)byte_at(q0 + k) << (8 * (k & 3));
-                v = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+            __syncthreads();
+            const int nlist = list_n;
+            drew = drew || nlist > 0;
+            for (int base = 0; base < nlist; base += TC_SETUP_CHUNK) {
+                const int nseg = min(TC_SETUP_CHUNK, nlist - base);
+                for (int i = tid; i < nseg * TC_MAX_PRIMS_PER_SEG; i += TC_RASTER_THREADS) prims[i].kind = TC_PRIM_NONE;
+                __syncthreads();
+                if (warp < TC_N_ROLES && lane < nseg) {
+                    int4 s4 = *(const int4 *)(a.seg + ((size_t)env * a.sum_edges + list_src[base + lane]) * 4);
+                    tc_polyline_setup(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, warp, prims + lane * TC_MAX_PRIMS_PER_SEG);
+                }
+                __syncthreads();
+                for (int p = warp; p < nseg * TC_MAX_PRIMS_PER_SEG; p += TC_RASTER_THREADS / 32)
+                    if (prims[p].kind != TC_PRIM_NONE) {
+                        TcPlane pl = {planes + (size_t)list_c[base + p / TC_MAX_PRIMS_PER_SEG] * a.plane_words, a.H, a.W, y_lo, y_hi, y_lo};
+                        tc_prim_draw(g, pl, prims[p]);
+                    }
+                __syncthreads();
             }
         }
-        tc_st_cs(o4 + j, v);
     }
-    for (size_t i = head + (nvec << 4) + threadIdx.x; i < nbytes; i += TC_RASTER_THREADS) out[i] = byte_at(i);
+    tc_store_rgb<TC_RASTER_THREADS>(out, (uint32_t)((y_hi - y_lo) * a.W), planes, (uint32_t)a.plane_words * 32u, C, color24, drew);
 }
-
 
 // ------------------------------------------------------------------------------------------------ fused camera pass + rasterise + store
 // classes, single band: a block per (env, class) runs the camera pass in shared memory, keeps the segments on chip,
@@ -439,6 +506,8 @@ struct TcRenderArgs {
     const int32_t *thickness;  // [N]
     const uint8_t *mask;       // optional
     uint8_t *obs;              // [N,C,H,W]
+    int rgb;                   // informational; the kernel is instantiated per format (needs all_classes): compose [H,W,3] layer colours, later classes on top (renderer.py:41-43)
+    uint8_t colors[TC_MAX_CLASSES * 3];
     int all_classes;           // 1: a block renders all C classes of an env (stacked C*H-row plane), 0: one class
     TcClassBlob all_desc;      // the union graph of all classes (all_classes == 1)
     int32_t edge_off[TC_MAX_CLASSES + 1];
@@ -452,7 +521,6 @@ __host__ __device__ inline size_t tc_render_union_bytes(int max_nodes, int max_c
     size_t a = tc_render_scratch_bytes(max_nodes) + (size_t)max_cblob_bytes, b = (size_t)plane_words * 4;
     return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
-#define TC_SETUP_CHUNK 16 // segments set up per round (one thread each), then drawn by all warps
 __host__ __device__ inline size_t tc_render_segs_bytes(int max_edges) { return (size_t)(max_edges > 0 ? max_edges : 1) * 16; }
 __host__ __device__ inline size_t tc_render_smem_bytes(int max_nodes, int max_edges, int max_cblob_bytes, int plane_words) {
     return tc_render_union_bytes(max_nodes, max_cblob_bytes, plane_words) + tc_render_segs_bytes(max_edges) +
@@ -461,12 +529,13 @@ __host__ __device__ inline size_t tc_render_smem_bytes(int max_nodes, int max_ed
 
 // NT threads per block: 256 for large frames (4 blocks/SM, stores dominate), 128 for small ones (8 blocks/SM: the block's
 // work is then the latency-bound camera pass, and twice as many independent blocks hide it better)
-template <int NT>
+template <int NT, bool RGB>
 __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const TcRenderArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int seg_cnt;
     __shared__ __align__(8) uint64_t bar;
     __shared__ double s_pose[12], s_cam[TC_CAM_N];
+    __shared__ uint32_t s_color24[TC_MAX_CLASSES];
     const int env = a.all_classes ? blockIdx.x : blockIdx.x / a.n_classes, c = a.all_classes ? 0 : blockIdx.x % a.n_classes;
     if (a.mask && !a.mask[env]) return;
     const int tid = threadIdx.x;
@@ -517,6 +586,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const 
         sc.vis = rB + np; sc.front = fA; sc.inr = rA;
         // pose and intrinsics go through shared memory: 17 doubles held in registers by every thread across the whole
         // camera pass would push the kernel over 64 registers, and spills are local-memory traffic behind the stores
+        if (RGB && tid >= 64 && tid < 64 + TC_MAX_CLASSES) {
+            const int cc = tid - 64;
+            s_color24[cc] = a.colors[3 * cc] | (a.colors[3 * cc + 1] << 8) | (a.colors[3 * cc + 2] << 16);
+        }
         if (tid < 12) s_pose[tid] = a.pose[(size_t)env * 12 + tid];
         else if (tid < 12 + (TC_CAM_MAX_RANGE - TC_CAM_FX + 1)) s_cam[TC_CAM_FX + tid - 12] = a.cam[(size_t)env * TC_CAM_N + TC_CAM_FX + tid - 12];
         __syncthreads();      // barrier init, pose and intrinsics visible to all threads
@@ -568,7 +641,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const 
     const int cnt = seg_cnt;
     TC_TL(tl2 = clock64());
     const int n_planes = a.all_classes ? a.n_classes : 1;
-    uint8_t *out = a.obs + ((size_t)env * a.n_classes + c) * a.H * a.W;
+    uint8_t *out = RGB ? a.obs + (size_t)env * a.H * a.W * 3 : a.obs + ((size_t)env * a.n_classes + c) * a.H * a.W;
     const size_t nbytes = (size_t)n_planes * a.H * a.W;
     if (cnt > 0) {
         for (int i = tid; i < a.plane_words; i += NT) plane[i] = 0;
@@ -604,7 +677,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const 
         }
     }
     TC_TL(tl3 = clock64());
-    tc_store_plane<NT>(out, nbytes, plane, cnt > 0);
+    if (RGB) tc_store_rgb<NT>(out, (uint32_t)(a.H * a.W), plane, (uint32_t)(a.H * a.W), a.n_classes, s_color24, cnt > 0);
+    else tc_store_plane<NT>(out, nbytes, plane, cnt > 0);
 #ifdef TC_TIMELINE
     if (a.timeline && tid == 0) {
         unsigned smid;
