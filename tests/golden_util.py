@@ -14,7 +14,8 @@ SCENARIOS = ["simple_rgb_smoke", "knuff_480_stanley", "knuff_mixed", "simple_84_
 class Golden:
     def __init__(self, name):
         self.name = name
-        self.d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
+            self.d = {k: z[k] for k in z.files}   # decompress once (NpzFile re-reads the zip member on every access)
         self.meta = json.loads(str(self.d["meta"]))
         self.cfg = self.meta["config"]
         self.F = len(self.d["ev_kind"])
