@@ -371,3 +371,44 @@ def test_cuda_checkpoint_restore_resumes_bit_for_bit():
 
     assert int(env2._spawn_cursor.sum()) + env2._resets_since_refill > 0
     env2.close()
+
+
+def test_cuda_grouped_resolutions_match_oracle():
+    """BASELINE config 5: per-env resolution via resolution groups (one dense tensor per group), per-env camera pitch / fov
+    and car parameters on top; global env indices (hence spawn seeds) run through the groups."""
+    from tinycarlo_b200 import TinyCarloGroupedVecEnv
+    groups = [(192, [84, 84]), (128, [128, 160]), (64, [240, 320])]
+    n = sum(g[0] for g in groups)
+    cfg = make_config("knuffingen", "classes")
+    rng = np.random.default_rng(31)
+    env = TinyCarloGroupedVecEnv(cfg, groups, device="cuda:0")
+    pitch = rng.integers(10, 20, n).astype(np.float64)
+    fov = rng.integers(90, 130, n).astype(np.float64)
+    env.set_camera_params(orientation=np.stack([pitch, np.zeros(n), np.zeros(n)], 1), fov=fov)
+    wb = rng.uniform(0.04, 0.06, n)
+    env.set_car_params(wheelbase=wb)
+    obs_list, info = env.reset(seed=3)
+    oenvs = []
+    for e, (cnt, res) in zip(env.envs, groups):
+        c = make_config("knuffingen", "classes", cam={"resolution": res})
+        o = oracle_env(c, cnt, cam_rows=e._cam_rows.copy(), car_rows=e._car_rows.copy())
+        o.reset(e._spawn_nodes.cpu().numpy())
+        oenvs.append(o)
+    # a sharded draw equals one flat draw: group g's env i is global env offsets[g] + i
+    from tinycarlo_b200.spawn import SpawnSampler
+    flat = SpawnSampler(env.envs[0].map, n, table_len=1).seed(3)[:, 0]
+    assert np.array_equal(np.concatenate([e._spawn_nodes.cpu().numpy() for e in env.envs]), flat)
+    for t in range(15):
+        cte = np.concatenate([o.cte for o in oenvs])
+        he = np.concatenate([o.heading_error for o in oenvs])
+        cc = stanley_actions(cte, he, cfg["car"]["max_steering_angle"])
+        cc[:, 1] += rng.normal(0, 0.2, n).astype(np.float32)
+        man = np.zeros(n, np.int32)
+        obs_list, reward, term, trunc, info = env.step({"car_control": torch.from_numpy(cc).cuda(), "maneuver": torch.from_numpy(man).cuda()})
+        torch.cuda.synchronize()
+        for o, sl, obs in zip(oenvs, env._slices(), obs_list):
+            o.step(cc[sl].astype(np.float64), man[sl])
+            assert np.array_equal(obs.cpu().numpy(), o.obs), t
+        np.testing.assert_allclose(info["cte"].cpu().numpy(), np.concatenate([o.cte for o in oenvs]), rtol=RTOL32, atol=1e-7)
+        assert np.array_equal(trunc.cpu().numpy(), np.concatenate([o.truncated for o in oenvs]).astype(bool))
+    env.close()

@@ -2,6 +2,7 @@
 
 Public surface:
   TinyCarloVecEnv   N envs in lockstep on one GPU, CUDA tensors in and out (tinycarlo_b200/vec_env.py)
+  TinyCarloGroupedVecEnv  several resolution groups presented as one env (per-env resolution, BASELINE config 5)
   TinyCarloEnv      single-env drop-in for the reference's gymnasium env (tinycarlo_b200/env.py), a batch of one
   tinycarlo_b200.wrapper   the reference's reward / termination wrappers, for both of the above
 `gym.make("tinycarlo-v2", config=...)` is registered when gymnasium is importable (soft dependency)."""
@@ -12,6 +13,9 @@ def __getattr__(name):
     if name == "TinyCarloVecEnv":
         from .vec_env import TinyCarloVecEnv
         return TinyCarloVecEnv
+    if name == "TinyCarloGroupedVecEnv":
+        from .grouped_env import TinyCarloGroupedVecEnv
+        return TinyCarloGroupedVecEnv
     if name == "TinyCarloEnv":
         from .env import TinyCarloEnv
         return TinyCarloEnv

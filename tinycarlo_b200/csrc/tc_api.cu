@@ -12,6 +12,16 @@
 #include "tc_kernels.cuh"
 #include "tc_pack.h"
 
+// Kernel attributes are per function, not per handle: several handles with different shared-memory needs coexist
+// (TinyCarloGroupedVecEnv), so every kernel is simply allowed the device maximum (227 KB opt-in on sm_100).
+template <typename K>
+static cudaError_t tc_allow_max_smem(K kernel) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
+}
+
 static thread_local std::string g_last_error;
 static int tc_fail(int code, const std::string &msg) {
     g_last_error = msg;
@@ -234,21 +244,20 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     }
     if (h->fused_ok) {
         if (const char *rt = getenv("TC_RENDER_THREADS")) h->render_threads = atoi(rt) == 128 ? 128 : 256;
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<128, false>));
         TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, false>));
         TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, true>));
         TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_rgb_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->track_smem));
-    TC_CUDAH(cudaFuncSetAttribute(tc_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->proj_smem));
-    TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->plane_words_cls * 4)));
-    TC_CUDAH(cudaFuncSetAttribute(tc_raster_rgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)tc_raster_rgb_smem_bytes(C, h->plane_words_rgb)));
+    TC_CUDAH(tc_allow_max_smem(tc_track_kernel));
+    TC_CUDAH(tc_allow_max_smem(tc_project_kernel));
+    TC_CUDAH(tc_allow_max_smem(tc_raster_classes_kernel));
+    TC_CUDAH(tc_allow_max_smem(tc_raster_rgb_kernel));
     *out = h;
     return TC_OK;
 }
