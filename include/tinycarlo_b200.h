@@ -56,7 +56,10 @@ enum { TC_SI_PATH_LEN = 0, TC_SI_LAST_MANEUVER = 1, TC_SI_PATH_NODES = 2 /* 4 x 
 enum { TC_CP_WHEELBASE = 0, TC_CP_TRACK_WIDTH, TC_CP_MAX_VELOCITY, TC_CP_MAX_STEERING_DEG, TC_CP_STEERING_SPEED /* NaN = None */,
        TC_CP_MAX_ACCELERATION /* NaN = None */, TC_CP_MAX_DECELERATION, TC_CP_DT, TC_CP_N = 8 };
 enum { TC_CAM_E = 0 /* 12: row-major 3x4 */, TC_CAM_FX = 12, TC_CAM_FY, TC_CAM_CX, TC_CAM_CY, TC_CAM_MAX_RANGE, TC_CAM_N = 20 };
-enum { TC_OBS_CLASSES = 0 /* u8 [N,C,H,W], 0/255 */, TC_OBS_RGB = 1 /* u8 [N,H,W,3], layer colours */ };
+enum { TC_OBS_CLASSES = 0 /* u8 [N,C,H,W], 0/255 */, TC_OBS_RGB = 1 /* u8 [N,H,W,3], layer colours */,
+       /* beyond the reference, same masks in the format a policy consumes: */
+       TC_OBS_CLASSES_BITS = 2 /* u32 [N,C,ceil(H*W/32)]: bit (y*W+x)%32 of word (y*W+x)/32 = pixel (x,y) */,
+       TC_OBS_CLASSES_BF16 = 3 /* bfloat16 [N,C,H,W], 0.0 / 1.0 */ };
 /* info_f64 row: cte, heading_error, velocity, reward, then C laneline distances */
 enum { TC_INFO_CTE = 0, TC_INFO_HEADING, TC_INFO_VELOCITY, TC_INFO_REWARD, TC_INFO_DIST0 = 4 };
 

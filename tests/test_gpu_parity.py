@@ -412,3 +412,30 @@ def test_cuda_grouped_resolutions_match_oracle():
         np.testing.assert_allclose(info["cte"].cpu().numpy(), np.concatenate([o.cte for o in oenvs]), rtol=RTOL32, atol=1e-7)
         assert np.array_equal(trunc.cpu().numpy(), np.concatenate([o.truncated for o in oenvs]).astype(bool))
     env.close()
+
+
+@pytest.mark.parametrize("res,n", [([128, 160], 512), ([480, 640], 64), ([84, 84], 256)])
+def test_cuda_policy_formats_equal_the_u8_masks(res, n):
+    """obs formats beyond the reference: "classes_bits" and "classes_bf16" carry exactly the u8 class masks."""
+    cfg = make_config("knuffingen", "classes", cam={"resolution": res})
+    envs = {f: _vec(cfg, n, obs_format=f) for f in ("classes", "classes_bf16")}
+    if (res[0] * res[1]) % 32 == 0:
+        envs["classes_bits"] = _vec(cfg, n, obs_format="classes_bits")
+    rng = np.random.default_rng(8)
+    for e in envs.values():
+        e.reset(seed=4)
+    H, W = res
+    for t in range(6):
+        cc = torch.from_numpy(np.stack([rng.uniform(0.3, 1, n), rng.uniform(-1, 1, n)], 1).astype(np.float32)).cuda()
+        man = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)).cuda()
+        for e in envs.values():
+            e.step({"car_control": cc, "maneuver": man})
+        ref = envs["classes"].obs
+        assert int((ref > 0).sum()) > 0
+        assert torch.equal((envs["classes_bf16"].obs.float() * 255).to(torch.uint8), ref)
+        if "classes_bits" in envs:
+            words = envs["classes_bits"].obs.cpu().numpy().view(np.uint32)           # [n, C, H*W/32]
+            bits = np.unpackbits(words.view(np.uint8), axis=-1, bitorder="little")[..., : H * W].reshape(n, -1, H, W)
+            assert np.array_equal(bits * 255, ref.cpu().numpy())
+    for e in envs.values():
+        e.close()

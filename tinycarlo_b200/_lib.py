@@ -14,7 +14,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
 
 TC_SF_N, TC_SI_N, TC_CP_N, TC_CAM_N = 8, 16, 8, 20
-TC_OBS_CLASSES, TC_OBS_RGB = 0, 1
+TC_OBS_CLASSES, TC_OBS_RGB, TC_OBS_CLASSES_BITS, TC_OBS_CLASSES_BF16 = 0, 1, 2, 3
 
 
 class TinyCarloError(RuntimeError):

@@ -133,7 +133,7 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     const int C = map->n_classes;
     if (C <= 0 || C > TC_MAX_CLASSES) return tc_fail(TC_ERR_INVALID, "tc_create: n_classes out of range (1..16)");
     if (sim->height <= 0 || sim->width <= 0) return tc_fail(TC_ERR_INVALID, "tc_create: bad resolution");
-    if (sim->obs_format != TC_OBS_CLASSES && sim->obs_format != TC_OBS_RGB) return tc_fail(TC_ERR_INVALID, "tc_create: bad obs_format");
+    if (sim->obs_format < TC_OBS_CLASSES || sim->obs_format > TC_OBS_CLASSES_BF16) return tc_fail(TC_ERR_INVALID, "tc_create: bad obs_format");
     TcPacked pk;
     {
         std::string err = tc_pack_map(map, pk);
@@ -244,12 +244,16 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     }
     if (h->fused_ok) {
         if (const char *rt = getenv("TC_RENDER_THREADS")) h->render_threads = atoi(rt) == 128 ? 128 : 256;
-        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<128, false>));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, false>));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, true>));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<128, TC_FMT_U8>));
+        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, TC_FMT_BITS>));
+        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, TC_FMT_BF16>));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, TC_FMT_BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, TC_FMT_BF16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128, TC_FMT_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, TC_FMT_U8>));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, TC_FMT_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, TC_FMT_RGB>));
+        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, TC_FMT_RGB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -295,7 +299,12 @@ int tc_set_wrapped(TcHandle *h, int32_t wrapped) {
 static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int obs_format, int32_t *seg_count_out, int32_t *seg_out,
                             cudaStream_t st, cudaEvent_t after_project = nullptr) {
     const int N = h->n_envs, C = h->C;
-    if (obs && h->fused_ok && !seg_count_out && !seg_out && (obs_format == TC_OBS_CLASSES || h->fused_all)) {
+    if (obs_format == TC_OBS_CLASSES_BITS || obs_format == TC_OBS_CLASSES_BF16) {
+        if (!h->fused_ok || seg_count_out || seg_out) return tc_fail(TC_ERR_INVALID, "bit-packed / bf16 observations need the fused render path (frame too large or debug segments requested)");
+        if (obs_format == TC_OBS_CLASSES_BF16 && (h->H * h->W) % 8 != 0) return tc_fail(TC_ERR_INVALID, "bf16 observations need H*W to be a multiple of 8");
+        if (obs_format == TC_OBS_CLASSES_BITS && h->fused_all && (h->H * h->W) % 32 != 0) return tc_fail(TC_ERR_INVALID, "bit-packed observations of small frames need H*W to be a multiple of 32");
+    }
+    if (obs && h->fused_ok && !seg_count_out && !seg_out && (obs_format != TC_OBS_RGB || h->fused_all)) {
         TcRenderArgs fa;
         fa.cblob_desc = h->d_cblob_desc; fa.cblob = h->d_cblob; fa.max_cblob_bytes = h->fused_cblob; fa.n_envs = N; fa.n_classes = C;
         fa.max_nodes = h->fused_nodes; fa.max_edges = h->fused_edges;
@@ -308,9 +317,11 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
         fa.timeline = mask ? nullptr : h->timeline;
         if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
         const int grid = h->fused_all ? N : N * C;
-        if (fa.rgb) tc_render_classes_kernel<256, true><<<grid, 256, h->render_smem, st>>>(fa);
-        else if (h->render_threads == 128) tc_render_classes_kernel<128, false><<<grid, 128, h->render_smem, st>>>(fa);
-        else tc_render_classes_kernel<256, false><<<grid, 256, h->render_smem, st>>>(fa);
+        if (obs_format == TC_OBS_RGB) tc_render_classes_kernel<256, TC_FMT_RGB><<<grid, 256, h->render_smem, st>>>(fa);
+        else if (obs_format == TC_OBS_CLASSES_BITS) tc_render_classes_kernel<256, TC_FMT_BITS><<<grid, 256, h->render_smem, st>>>(fa);
+        else if (obs_format == TC_OBS_CLASSES_BF16) tc_render_classes_kernel<256, TC_FMT_BF16><<<grid, 256, h->render_smem, st>>>(fa);
+        else if (h->render_threads == 128) tc_render_classes_kernel<128, TC_FMT_U8><<<grid, 128, h->render_smem, st>>>(fa);
+        else tc_render_classes_kernel<256, TC_FMT_U8><<<grid, 256, h->render_smem, st>>>(fa);
         h->launches++;
         TC_CUDA(cudaGetLastError());
         return TC_OK;
@@ -414,7 +425,7 @@ int tc_render(TcHandle *h, const uint8_t *dev_mask, uint8_t *dev_obs, int32_t ob
               void *stream) {
     if (!h) return tc_fail(TC_ERR_INVALID, "tc_render: null handle");
     if (!h->cam_set) return tc_fail(TC_ERR_STATE, "tc_render: camera parameters not set");
-    if (obs_format != TC_OBS_CLASSES && obs_format != TC_OBS_RGB) return tc_fail(TC_ERR_INVALID, "tc_render: bad obs_format");
+    if (obs_format < TC_OBS_CLASSES || obs_format > TC_OBS_CLASSES_BF16) return tc_fail(TC_ERR_INVALID, "tc_render: bad obs_format");
     TC_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     tc_pose_kernel<<<(h->n_envs + 127) / 128, 128, 0, st>>>(h->n_envs, h->d_sf, h->d_cam, h->d_pose);

@@ -392,6 +392,33 @@ __device__ __forceinline__ void tc_store_rgb(uint8_t *out, uint32_t npx, const u
     for (uint32_t i = head + (nvec << 4) + tid; i < nbytes; i += NT) out[i] = byte_at(i);
 }
 
+// Observation formats of the fused kernel beyond the reference's two (emit what the policy consumes):
+//   BITS  the bit plane itself, 1 bit per pixel (bit i of the little-endian byte stream = pixel i, i = y*W + x): 8x fewer bytes
+//   BF16  0.0 / 1.0 in bfloat16 [N,C,H,W]: the u8 -> float /255 normalisation kernel of the consumer disappears
+enum { TC_FMT_U8 = 0, TC_FMT_RGB = 1, TC_FMT_BITS = 2, TC_FMT_BF16 = 3 };
+
+template <int NT>
+__device__ __forceinline__ void tc_store_bits(uint32_t *out, int words, const uint32_t *plane, bool any) {
+    for (int i = threadIdx.x; i < words; i += NT) out[i] = any ? plane[i] : 0u;
+}
+// 8 pixels -> 8 bfloat16 (0x3F80 = 1.0) = one 16-byte store; the caller guarantees 16-byte alignment and npx % 8 == 0
+template <int NT>
+__device__ __forceinline__ void tc_store_bf16(uint16_t *out, uint32_t npx, const uint32_t *plane, bool any) {
+    uint4 *o4 = (uint4 *)out;
+    const uint32_t nvec = npx >> 3;
+    for (uint32_t j = threadIdx.x; j < nvec; j += NT) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (any) {
+            uint32_t b = (plane[(8u * j) >> 5] >> ((8u * j) & 31)) & 0xffu;
+            if (b) {
+                auto two = [](uint32_t q) { return ((q & 1u) ? 0x3F80u : 0u) | ((q & 2u) ? 0x3F800000u : 0u); };
+                v = make_uint4(two(b), two(b >> 2), two(b >> 4), two(b >> 6));
+            }
+        }
+        tc_st_cs(o4 + j, v);
+    }
+}
+
 // classes: grid = N*C*n_bands blocks; each owns rows [y_lo, y_hi) of one class plane
 __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_classes_kernel(const TcRasterArgs a) {
     extern __shared__ __align__(16) uint32_t plane[];
@@ -529,8 +556,9 @@ __host__ __device__ inline size_t tc_render_smem_bytes(int max_nodes, int max_ed
 
 // NT threads per block: 256 for large frames (4 blocks/SM, stores dominate), 128 for small ones (8 blocks/SM: the block's
 // work is then the latency-bound camera pass, and twice as many independent blocks hide it better)
-template <int NT, bool RGB>
+template <int NT, int FMT>
 __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const TcRenderArgs a) {
+    constexpr bool RGB = FMT == TC_FMT_RGB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int seg_cnt;
     __shared__ __align__(8) uint64_t bar;
@@ -677,7 +705,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const 
         }
     }
     TC_TL(tl3 = clock64());
-    if (RGB) tc_store_rgb<NT>(out, (uint32_t)(a.H * a.W), plane, (uint32_t)(a.H * a.W), a.n_classes, s_color24, cnt > 0);
+    if (FMT == TC_FMT_RGB) tc_store_rgb<NT>(out, (uint32_t)(a.H * a.W), plane, (uint32_t)(a.H * a.W), a.n_classes, s_color24, cnt > 0);
+    else if (FMT == TC_FMT_BITS) {
+        // planes are whole words here (the host only selects this format when H*W % 32 == 0 or one class per block)
+        const int words = (int)(((size_t)a.H * a.W + 31) / 32) * n_planes;
+        tc_store_bits<NT>((uint32_t *)a.obs + ((size_t)env * a.n_classes + c) * (((size_t)a.H * a.W + 31) / 32), words, plane, cnt > 0);
+    } else if (FMT == TC_FMT_BF16)
+        tc_store_bf16<NT>((uint16_t *)a.obs + ((size_t)env * a.n_classes + c) * a.H * a.W, (uint32_t)(n_planes * a.H * a.W), plane, cnt > 0);
     else tc_store_plane<NT>(out, nbytes, plane, cnt > 0);
 #ifdef TC_TIMELINE
     if (a.timeline && tid == 0) {

@@ -59,9 +59,15 @@ class TinyCarloVecEnv:
         self.no_observation = False
         N, Cn = self.num_envs, self.n_classes
         dev = self.device
-        fmt = _lib.TC_OBS_CLASSES if self.observation_space_format != "rgb" else _lib.TC_OBS_RGB
+        fmt = {"rgb": _lib.TC_OBS_RGB, "classes_bits": _lib.TC_OBS_CLASSES_BITS, "classes_bf16": _lib.TC_OBS_CLASSES_BF16}.get(
+            self.observation_space_format, _lib.TC_OBS_CLASSES)
         self._fmt = fmt
-        self.obs_shape = (Cn, self.H, self.W) if fmt == _lib.TC_OBS_CLASSES else (self.H, self.W, 3)
+        # "classes" (u8 0/255, the reference's format), "rgb", and two formats a policy can consume directly:
+        # "classes_bits": int32 [N,C,ceil(H*W/32)], bit (y*W+x)%32 of word (y*W+x)/32 is pixel (x,y)  (8x fewer bytes)
+        # "classes_bf16": bfloat16 [N,C,H,W] with 0.0 / 1.0
+        self.obs_shape = {_lib.TC_OBS_CLASSES: (Cn, self.H, self.W), _lib.TC_OBS_RGB: (self.H, self.W, 3),
+                          _lib.TC_OBS_CLASSES_BITS: (Cn, (self.H * self.W + 31) // 32), _lib.TC_OBS_CLASSES_BF16: (Cn, self.H, self.W)}[fmt]
+        self.obs_dtype = {_lib.TC_OBS_CLASSES_BITS: torch.int32, _lib.TC_OBS_CLASSES_BF16: torch.bfloat16}.get(fmt, torch.uint8)
 
         # ---- library handle (map tables go to the device once)
         m = self.map
@@ -78,7 +84,7 @@ class TinyCarloVecEnv:
 
         # ---- outputs (allocated once; step()/reset() return views)
         with torch.cuda.device(dev):
-            self.obs = torch.zeros((N,) + self.obs_shape, dtype=torch.uint8, device=dev)
+            self.obs = torch.zeros((N,) + self.obs_shape, dtype=self.obs_dtype, device=dev)
             f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
             self.out = {"cte": f32(N), "heading_error": f32(N), "velocity": f32(N), "reward": f32(N), "position": f32(N, 2),
                         "orientation": f32(N), "laneline_distances": f32(N, Cn),

@@ -47,3 +47,27 @@ run("config1-like simple_layout 480x640 rgb random", make_config("simple_layout"
 run("config3 knuffingen 480x640 classes stanley", make_config("knuffingen", "classes", cam={"resolution": [480, 640]}), 16384, policy="stanley")
 run("config5-like knuffingen 128x160 per-env params", make_config("knuffingen", "classes", cam={"resolution": [128, 160]}), 32768, policy="stanley", per_env=True)
 run("knuffingen 128x160 classes (shipped resolution)", make_config("knuffingen", "classes"), 32768, policy="stanley")
+
+
+def run_fmt(fmt):
+    cfg = make_config("knuffingen", "classes", cam={"resolution": [480, 640]})
+    n = 16384
+    env = TinyCarloVecEnv(cfg, n, device="cuda:0", autoreset="next_step", obs_format=fmt)
+    env.reset(seed=0)
+    cc = torch.zeros((n, 2), device="cuda"); cc[:, 0] = 0.8; man = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for _ in range(5):
+        env.step({"car_control": cc, "maneuver": man})
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        env.step({"car_control": cc, "maneuver": man})
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    nb = env.obs[0].numel() * env.obs.element_size()
+    print(f"knuffingen 480x640 obs_format={fmt:14s} N={n} obs={nb:8d} B {ms:8.3f} ms/step {n / ms * 1e3 / 1e6:8.2f} M env-steps/s {n * nb / ms / 1e6:8.1f} GB/s")
+    env.close()
+
+
+for f in ("classes", "classes_bits", "classes_bf16"):
+    run_fmt(f)
