@@ -255,6 +255,36 @@ def main():
         w1.record()
         torch.cuda.synchronize(dev)
         write_ceiling = max(write_ceiling, env.obs.numel() / (w0.elapsed_time(w1) * 1e-3) / 1e9)
+    # ---- the same host loop WITH the observations copied to pinned host memory every step (what the single-env gymnasium
+    # drop-in does), on a reduced batch so that it stays a measurement of the path and not of minutes of PCIe: rank 0 only
+    e2e_obs = None
+    if not args.no_e2e and rank == 0:
+        n_small = min(N, 512)
+        env_s = TinyCarloVecEnv(cfg, n_small, device=dev, autoreset="next_step")
+        env_s.reset(seed=0)
+        h_obs = torch.zeros(env_s.obs.shape, dtype=torch.uint8).pin_memory()
+        hs = [torch.zeros((n_small, 2), dtype=torch.float32).pin_memory(), torch.zeros(n_small, dtype=torch.int32).pin_memory(),
+              torch.zeros(n_small, dtype=torch.float32).pin_memory(), torch.zeros(n_small, dtype=torch.uint8).pin_memory(),
+              torch.zeros(n_small, dtype=torch.uint8).pin_memory(), torch.zeros(n_small, dtype=torch.float32).pin_memory(),
+              torch.zeros(n_small, dtype=torch.float32).pin_memory()]
+        hs[0][:, 0] = speed
+
+        def step_host_obs():
+            hs[0].numpy()[:, 1] = (hs[6].numpy() + np.arctan2(k_gain * hs[5].numpy(), speed)) * (180.0 / np.pi / max_steer)
+            env_s.step_host(*hs)
+            h_obs.copy_(env_s.obs, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        for _ in range(2):
+            step_host_obs()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host_obs()
+        dt_s = time.perf_counter() - t0
+        e2e_obs = {"value": n_small * args.steps / dt_s, "unit": UNIT, "envs": n_small, "h2d_bytes_per_step": n_small * 12,
+                   "d2h_bytes_per_step": n_small * 14 + int(h_obs.numel()),
+                   "note": "as e2e, plus the u8 observations copied to pinned host memory every step (PCIe-bound)"}
+        env_s.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -270,7 +300,16 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     raster_ms = kern_ms["raster"] / max(kern_steps, 1)
     achieved = N * OBS_BYTES / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM traffic of that kernel from the committed ncu capture (profiles/r01_traffic.json: dram__bytes_read.sum +
+    # dram__bytes_write.sum of one launch, per env), scaled to this launch's env count; null if the file is missing
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f)["render_kernel_dram_bytes_per_env"] * N
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes": N * OBS_BYTES,
                 "kernel": "tc_render_classes_kernel", "kernel_ms_per_launch": raster_ms,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "step_share_ms": {k: v / max(kern_steps, 1) for k, v in kern_ms.items()},
@@ -289,7 +328,7 @@ def main():
             "config": {"workload": workload, "obs_bytes_per_env_step": OBS_BYTES, "envs_total": N * world,
                        "l2": "observation tensor (25 GB/GPU) is far larger than L2; nothing is re-read between steps",
                        "obs_gbs": value * OBS_BYTES / 1e9},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "e2e": e2e, "e2e_obs_to_host": e2e_obs, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "episode_stats": {"finished": float(stats[0].item()), "truncated": float(stats[1].item()), "reward_sum": float(stats[2].item())}}
     print(json.dumps(line), flush=True)
     if world > 1:
