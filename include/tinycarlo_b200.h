@@ -139,6 +139,15 @@ TC_API int tc_step_host(TcHandle *h, const float *host_car_control, const int32_
                  float *host_reward, uint8_t *host_terminated, uint8_t *host_truncated, float *host_cte, float *host_heading_error,
                  void *stream);
 
+/* NoiseObservationWrapper (tinycarlo/wrapper/observation.py:5-33) on u8 class observations [N,C,H,W], in place: per class
+ * n_blobs filled circles (centre uniform in the frame, radius uniform in [1, max_radius)), each with probability 0.3 ORs in
+ * the pixels of a random class inside the circle, else erases the circle; classes ascending, blobs in sequence, like the
+ * reference. The reference draws from numpy's unseeded global RNG; here the draw of (env, step, class, blob) is
+ * Philox4x32-10 with key = seed and counter = (env_index_offset + env, step, class * n_blobs + blob, 0):
+ * x = r0 % W, y = r1 % H, radius = 1 + r2 % (max_radius - 1), copy = (r3 & 0xffff) < 19661, source class = (r3 >> 16) % C. */
+TC_API int tc_noise_blobs(TcHandle *h, uint8_t *dev_obs, uint64_t seed, uint32_t step, int32_t n_blobs, int32_t max_radius,
+                          int32_t env_index_offset, const uint8_t *dev_mask, void *stream);
+
 /* Number of kernel launches issued through this handle since creation (bench.py reports it). */
 TC_API int64_t tc_launch_count(const TcHandle *h);
 

@@ -481,6 +481,21 @@ int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline) {
     return TC_OK;
 }
 
+int tc_noise_blobs(TcHandle *h, uint8_t *dev_obs, uint64_t seed, uint32_t step, int32_t n_blobs, int32_t max_radius, int32_t env_index_offset,
+                   const uint8_t *dev_mask, void *stream) {
+    if (!h || !dev_obs) return tc_fail(TC_ERR_INVALID, "tc_noise_blobs: null argument");
+    if (n_blobs < 0 || max_radius < 1 || max_radius > 1023) return tc_fail(TC_ERR_INVALID, "tc_noise_blobs: max_radius must be in 1..1023, n_blobs >= 0");
+    TC_CUDA(cudaSetDevice(h->device));
+    TcNoiseArgs na;
+    na.n_envs = h->n_envs; na.n_classes = h->C; na.H = h->H; na.W = h->W; na.n_blobs = n_blobs; na.max_radius = max_radius;
+    na.seed_lo = (uint32_t)seed; na.seed_hi = (uint32_t)(seed >> 32); na.step = step; na.env_offset = (uint32_t)env_index_offset;
+    na.mask = dev_mask; na.obs = dev_obs;
+    tc_noise_blobs_kernel<<<h->n_envs, 256, 0, (cudaStream_t)stream>>>(na);
+    h->launches++;
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
 int64_t tc_launch_count(const TcHandle *h) { return h ? h->launches : 0; }
 
 int tc_profile_begin(TcHandle *h, int32_t max_steps) {

@@ -725,6 +725,79 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const 
 #undef TC_TL
 }
 
+// ------------------------------------------------------------------------------------------------ blob noise
+// NoiseObservationWrapper (tinycarlo/wrapper/observation.py:14-27) on the device: per class, n_blobs filled circles that
+// either erase the class mask or OR in the pixels of a randomly chosen class, applied in the reference's order (classes
+// ascending, blobs in sequence, in place: a blob sees what earlier blobs did). The reference draws from the unseeded global
+// numpy RNG; here every draw is a pure function of (seed, global env index, step, class, blob) through Philox4x32-10, so
+// runs are reproducible and independent of the sharding. cv2.circle(..., -1) is the midpoint circle of tc_circle_filled.
+__host__ __device__ inline void tc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct TcNoiseArgs {
+    int n_envs, n_classes, H, W;
+    int n_blobs, max_radius;
+    uint32_t seed_lo, seed_hi, step, env_offset;
+    const uint8_t *mask; // optional
+    uint8_t *obs;        // [N,C,H,W] u8
+};
+
+__global__ void __launch_bounds__(256) tc_noise_blobs_kernel(const TcNoiseArgs a) {
+    __shared__ int hw[1024]; // half width of the filled midpoint circle per |row offset| (radius < 1024)
+    __shared__ int bx, by, brad, bcopy, bsrc;
+    const int env = blockIdx.x, tid = threadIdx.x;
+    if (a.mask && !a.mask[env]) return;
+    const size_t plane = (size_t)a.H * a.W;
+    uint8_t *base = a.obs + (size_t)env * a.n_classes * plane;
+    for (int c = 0; c < a.n_classes; c++)
+        for (int k = 0; k < a.n_blobs; k++) {
+            if (tid == 0) {
+                uint32_t r[4];
+                tc_philox4x32_10((uint32_t)env + a.env_offset, a.step, (uint32_t)(c * a.n_blobs + k), 0u, a.seed_lo, a.seed_hi, r);
+                bx = (int)(r[0] % (uint32_t)a.W);
+                by = (int)(r[1] % (uint32_t)a.H);
+                brad = a.max_radius > 1 ? 1 + (int)(r[2] % (uint32_t)(a.max_radius - 1)) : 1;   // randint(1, max_radius)
+                bcopy = (r[3] & 0xffffu) < 19661u;                                               // p = 0.3
+                bsrc = (int)((r[3] >> 16) % (uint32_t)a.n_classes);
+                for (int i = 0; i <= brad; i++) hw[i] = -1;
+                int err = 0, dx = brad, dy = 0, plus = 1, minus = (brad << 1) - 1;
+                while (dx >= dy) {
+                    hw[dy] = max(hw[dy], dx);
+                    hw[dx] = max(hw[dx], dy);
+                    dy++; err += plus; plus += 2;
+                    int m = (err <= 0) - 1;
+                    err -= minus & m; dx += m; minus -= m & 2;
+                }
+            }
+            __syncthreads();
+            const int x = bx, y = by, rad = brad, src = bsrc;
+            const bool copy = bcopy != 0;
+            uint8_t *dst = base + (size_t)c * plane;
+            const uint8_t *sp = base + (size_t)src * plane;
+            if (!(copy && src == c)) {
+                const int side = 2 * rad + 1;
+                for (int i = tid; i < side * side; i += 256) {
+                    int ry = i / side - rad, rx = i % side - rad;
+                    int h = hw[ry < 0 ? -ry : ry];
+                    if (h < 0 || rx < -h || rx > h) continue;
+                    int px = x + rx, py = y + ry;
+                    if ((unsigned)px >= (unsigned)a.W || (unsigned)py >= (unsigned)a.H) continue;
+                    size_t o = (size_t)py * a.W + px;
+                    if (copy) dst[o] |= sp[o];
+                    else dst[o] = 0;
+                }
+            }
+            __syncthreads();
+        }
+}
+
 // ------------------------------------------------------------------------------------------------ test hook
 // layer.py known-answer queries on class 0 (tests only)
 __global__ void tc_debug_layer_kernel(const unsigned char *blob, TcBlobLayout L, int op, double px, double py, double ang, int i0, int i1,
