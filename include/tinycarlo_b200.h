@@ -55,6 +55,8 @@ enum { TC_SF_X = 0, TC_SF_Y, TC_SF_ROT, TC_SF_STEER_DEG, TC_SF_VEL, TC_SF_FRONT_
 enum { TC_SI_PATH_LEN = 0, TC_SI_LAST_MANEUVER = 1, TC_SI_PATH_NODES = 2 /* 4 x (n0,n1) */, TC_SI_PATH_EDGES = 10 /* 4 */, TC_SI_N = 16 };
 enum { TC_CP_WHEELBASE = 0, TC_CP_TRACK_WIDTH, TC_CP_MAX_VELOCITY, TC_CP_MAX_STEERING_DEG, TC_CP_STEERING_SPEED /* NaN = None */,
        TC_CP_MAX_ACCELERATION /* NaN = None */, TC_CP_MAX_DECELERATION, TC_CP_DT, TC_CP_N = 8 };
+/* spawn stream row (uint64): PCG64 state hi, lo, increment hi, lo, buffered 32-bit half (bit 32 = valid) */
+enum { TC_RNG_HI = 0, TC_RNG_LO, TC_RNG_INC_HI, TC_RNG_INC_LO, TC_RNG_BUF, TC_RNG_N = 5 };
 enum { TC_CAM_E = 0 /* 12: row-major 3x4 */, TC_CAM_FX = 12, TC_CAM_FY, TC_CAM_CX, TC_CAM_CY, TC_CAM_MAX_RANGE, TC_CAM_N = 20 };
 enum { TC_OBS_CLASSES = 0 /* u8 [N,C,H,W], 0/255 */, TC_OBS_RGB = 1 /* u8 [N,H,W,3], layer colours */,
        /* beyond the reference, same masks in the format a policy consumes: */
@@ -114,16 +116,25 @@ TC_API int tc_set_car_params(TcHandle *h, const double *dev_params /*[N,TC_CP_N]
 TC_API int tc_set_camera_params(TcHandle *h, const double *dev_cam /*[N,TC_CAM_N]*/, const int32_t *dev_thickness /*[N]*/, void *stream);
 TC_API int tc_set_wrapped(TcHandle *h, int32_t wrapped); /* 1: reward 0 / terminated false (env.py:137-138) */
 
+/* Spawn streams on the device (Map.sample_spawn's draw, map.py:61-64, under gymnasium seeding): dev_rng_state is uint64
+ * [N,5] per env = PCG64 state hi, lo, increment hi, lo, buffered 32-bit half (bit 32 = valid) of
+ * numpy.random.Generator(PCG64(SeedSequence(seed_i))); the host seeds it (tinycarlo_b200/pcg64.py) and the reset paths
+ * advance it exactly like numpy does for choice(spawn_points) / integers(0, n_nodes-1), redrawing while the node has no
+ * successor. dev_spawn_points: the config's map.spawn_points (n_spawn_points = 0: none). dev_last_spawn (optional, int32
+ * [N]) receives the node of each env's most recent reset. All buffers are caller-owned and must stay alive. */
+TC_API int tc_set_spawn_rng(TcHandle *h, uint64_t *dev_rng_state, const int32_t *dev_spawn_points, int32_t n_spawn_points,
+                            int32_t *dev_last_spawn);
+
 /* Next-step autoreset (gymnasium AutoresetMode.NEXT_STEP) inside tc_step: an env whose flag dev_done[i] is set is reset
  * by the step instead of being advanced (its action is ignored; reward 0, not terminated, not truncated, empty info, obs
- * of the spawn pose), taking lanepath node dev_spawn_table[i][dev_cursor[i]] and incrementing the cursor; every step
- * then rewrites dev_done[i] = terminated | truncated. All three buffers are caller-owned device memory that must stay
- * alive; the caller may OR further termination conditions (wrappers) into dev_done between steps. NULL dev_done = off. */
-TC_API int tc_set_autoreset(TcHandle *h, uint8_t *dev_done /*[N]*/, const int32_t *dev_spawn_table /*[N,table_len]*/, int32_t table_len,
-                            int32_t *dev_cursor /*[N]*/);
+ * of the spawn pose), drawing its spawn node from its device stream (tc_set_spawn_rng first); every step then rewrites
+ * dev_done[i] = terminated | truncated. dev_done is caller-owned device memory that must stay alive; the caller may OR
+ * further termination conditions (wrappers) into it between steps. NULL = off. */
+TC_API int tc_set_autoreset(TcHandle *h, uint8_t *dev_done /*[N]*/);
 
-/* Reset the envs with dev_mask[i] != 0 (NULL = all) to lanepath node dev_spawn_nodes[i]; renders into obs if non-NULL
- * and zeroes their info outputs like the reference's reset (car.py:47-51). */
+/* Reset the envs with dev_mask[i] != 0 (NULL = all) to lanepath node dev_spawn_nodes[i], or - dev_spawn_nodes NULL - to a
+ * node drawn from the env's device stream; renders into obs if non-NULL and zeroes their info outputs like the
+ * reference's reset (car.py:47-51). */
 TC_API int tc_reset(TcHandle *h, const uint8_t *dev_mask, const int32_t *dev_spawn_nodes, const TcOutputs *outs, void *stream);
 TC_API int tc_step(TcHandle *h, const float *dev_car_control /*[N,2]*/, const int32_t *dev_maneuver /*[N]*/, const TcOutputs *outs, void *stream);
 /* tc_step with float64 actions (the reference computes in float64 when it is fed Python floats). */

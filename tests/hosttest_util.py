@@ -35,6 +35,8 @@ def ht():
         L.ht_map_destroy.argtypes = [vp]
         L.ht_track.argtypes = [vp, i, i, i] + [vp] * 13
         L.ht_render.argtypes = [vp, i, i, i, i, i] + [vp] * 7
+        L.ht_spawn_draws.argtypes = [vp, i, vp, vp, i, i, vp]
+        L.ht_pcg_bounded.argtypes = [i, vp, C.c_uint32, i, vp]
         L.ht_polyline.argtypes = [vp, i, i, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i, i, i, i]
         _ht = L
     return _ht

@@ -2,6 +2,7 @@
 group; tests/hosttest_util.py): the node-parallel clip passes, the closed-form rasteriser and the CSR-based tracking are
 replayed against the reference's golden traces and fuzzed against cv2 / the oracle. The product never uses this build."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -118,3 +119,38 @@ def test_bitplane_bands_compose_to_full_frame():
         for y in range(0, H, 32):
             parts |= polyline(H, W, p0, p1, t, y_lo=y, y_hi=min(H, y + 32), nlanes=32)
         assert np.array_equal(full, parts), (p0, p1, t)
+
+
+def test_device_spawn_streams_equal_numpy_and_reference_draws():
+    """tc_pcg_bounded / tc_spawn_draw (the code the reset paths of the tracking kernel run, host build) against numpy's
+    Generator itself and against the spawn nodes recorded from the reference (map.py:51-69 under gymnasium seeding)."""
+    import ctypes as C
+    from hosttest_util import HostCore, P, ht
+    from tinycarlo_b200.pcg64 import VecPCG64
+    from tinycarlo_b200.spawn import spawn_stream_states
+    from pair_util import SPAWN_KNUFF, SPAWN_SIMPLE
+    from golden_util import GOLDEN_DIR
+    seeds = np.array(list(range(0, 64)) + [2**32 - 1, 2**32 + 5, 2**63 + 7, 2**64 - 1], dtype=np.uint64)
+    st = VecPCG64(seeds).device_rows()
+    gens = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(int(s)))) for s in seeds]
+    for hi in [21, 16, 429, 428, 2**31 + 1, 3, 2**32 - 1, 1, 7, 100000, 21]:   # 2^31+1: ~50 % rejection (uint32 argument)
+        out = np.zeros((len(seeds), 3), np.uint32)
+        ht().ht_pcg_bounded(len(seeds), P(st), hi, 3, P(out))
+        want = np.array([[int(g.integers(0, hi)) for _ in range(3)] for g in gens], dtype=np.uint32)
+        assert np.array_equal(out, want), hi
+    # the state rows round-trip through the host model (checkpoints)
+    v = VecPCG64()
+    v.load_device_rows(st)
+    assert np.array_equal(v.bounded(1000), np.array([int(g.integers(0, 1000)) for g in gens]))
+
+    d = np.load(os.path.join(GOLDEN_DIR, "spawn_draws.npz"))
+    for key, (mname, ppm, sp) in {"knuffingen_default": ("knuffingen", 222, SPAWN_KNUFF), "knuffingen_none": ("knuffingen", 222, None),
+                                  "simple_layout_default": ("simple_layout", 450, SPAWN_SIMPLE), "simple_layout_none": ("simple_layout", 450, None)}.items():
+        t = MapTables(resolve_map_path({"map_name": mname}, None), ppm, sp)
+        want = d[key]                      # [64 seeds, 12 consecutive resets]
+        core = HostCore(t, 1, np.zeros(8), np.zeros(20), 1, 8, 8)
+        st = spawn_stream_states(40, 10, env_index_offset=3)   # env i = the reference's stream for seed 13 + i
+        out = np.zeros((40, 12), np.int32)
+        spp = None if sp is None else np.asarray(sp, np.int32)
+        ht().ht_spawn_draws(core.h, 40, P(st), P(spp), 0 if sp is None else len(sp), 12, P(out))
+        assert np.array_equal(out, want[13:53]), key

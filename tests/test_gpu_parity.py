@@ -261,19 +261,23 @@ def test_cuda_autoreset_next_step_matches_oracle():
     empty info, reset observation). Emulated on the oracle with explicit resets on the same spawn nodes."""
     n, steps = 1024, 60
     cfg = make_config("simple_layout", "classes", cam={"resolution": [84, 84]}, car={"max_velocity": 0.15})
-    env = _vec(cfg, n, autoreset="next_step", spawn_table_len=8)   # small table: exercises the refill path
+    env = _vec(cfg, n, autoreset="next_step")
     oenv = oracle_env(cfg, n)
     rng = np.random.default_rng(321)
     env.reset(seed=9)
-    oenv.reset(env._spawn_nodes.cpu().numpy())
+    # the device streams against their host model (numpy-compatible PCG64 per env): column k = node of an env's k-th reset
+    from tinycarlo_b200.spawn import SpawnSampler
+    host_draws = SpawnSampler(env.map, n, table_len=32).seed(9)
+    n_drawn = np.ones(n, np.int64)
+    assert np.array_equal(env._spawn_nodes.cpu().numpy(), host_draws[:, 0])
+    oenv.reset(host_draws[:, 0])
     done = np.zeros(n, bool)
     n_resets = 0
     for t in range(steps):
         cc = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
         man = rng.integers(0, 4, n).astype(np.int32)
-        env._refill_spawn_table_if_due()   # what step() will do; read the table it is going to use
-        tab, cur = env._spawn_table.cpu().numpy(), env._spawn_cursor.cpu().numpy()
-        nodes = tab[np.arange(n), np.minimum(cur, tab.shape[1] - 1)]
+        nodes = host_draws[np.arange(n), n_drawn]   # what a finished env must draw inside this step
+        n_drawn[done] += 1
         obs, reward, term, trunc, info = env.step({"car_control": torch.from_numpy(cc).cuda(), "maneuver": torch.from_numpy(man).cuda()})
         # oracle: step the live envs, reset the finished ones
         keep_sf, keep_si, keep_obs = oenv.sf.copy(), oenv.si.copy(), oenv.obs.copy()
@@ -293,6 +297,7 @@ def test_cuda_autoreset_next_step_matches_oracle():
         assert np.array_equal(st["si"].cpu().numpy()[:, :10], oenv.si[:, :10])
         done = (oenv.terminated | oenv.truncated).astype(bool)
         assert np.array_equal(env.done_flags.cpu().numpy().astype(bool), done)
+        assert np.array_equal(env._spawn_nodes.cpu().numpy(), host_draws[np.arange(n), n_drawn - 1]), "device spawn draw"
     assert n_resets > 0
     env.close()
 
@@ -344,7 +349,7 @@ def test_cuda_checkpoint_restore_resumes_bit_for_bit():
     rng = np.random.default_rng(5)
     acts = [(torch.from_numpy(rng.uniform(-1, 1, (n, 2)).astype(np.float32)).cuda(), torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)).cuda())
             for _ in range(90)]
-    env = _vec(cfg, n, autoreset="next_step", spawn_table_len=4)
+    env = _vec(cfg, n, autoreset="next_step")
     env.reset(seed=77)
     for cc, man in acts[:40]:
         env.step({"car_control": cc, "maneuver": man})
@@ -357,7 +362,7 @@ def test_cuda_checkpoint_restore_resumes_bit_for_bit():
         obs, r, te, tr, _ = env.step({"car_control": cc, "maneuver": man})
         tail_a.append((obs.clone(), r.clone(), te.clone(), tr.clone(), env.out["info_f64"].clone()))
     env.close()
-    env2 = _vec(cfg, n, autoreset="next_step", spawn_table_len=4)
+    env2 = _vec(cfg, n, autoreset="next_step")
     env2.reset(seed=1)          # different streams, then overwritten by the checkpoint
     env2.restore(ck)
     for k, ((cc, man), want) in enumerate(zip(acts[40:], tail_a)):
@@ -369,7 +374,7 @@ def test_cuda_checkpoint_restore_resumes_bit_for_bit():
         assert torch.equal(r, want[1]), "reward"
         assert torch.equal(obs, want[0]), "obs"
 
-    assert int(env2._spawn_cursor.sum()) + env2._resets_since_refill > 0
+    assert not torch.equal(env2._rng_state.cpu(), ck["spawn_rng"]), "no spawn draw happened after the checkpoint"
     env2.close()
 
 

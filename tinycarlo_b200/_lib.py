@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("TC_LIB") or os.path.join(LIB_DIR, "libtinycarlo_b200.
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
 
-TC_SF_N, TC_SI_N, TC_CP_N, TC_CAM_N = 8, 16, 8, 20
+TC_SF_N, TC_SI_N, TC_CP_N, TC_CAM_N, TC_RNG_N = 8, 16, 8, 20, 5
 TC_OBS_CLASSES, TC_OBS_RGB, TC_OBS_CLASSES_BITS, TC_OBS_CLASSES_BF16 = 0, 1, 2, 3
 
 
@@ -79,7 +79,8 @@ def lib():
     L.tc_set_car_params.argtypes = [vp, vp, vp]
     L.tc_set_camera_params.argtypes = [vp, vp, vp, vp]
     L.tc_set_wrapped.argtypes = [vp, i32]
-    L.tc_set_autoreset.argtypes = [vp, vp, vp, i32, vp]
+    L.tc_set_autoreset.argtypes = [vp, vp]
+    L.tc_set_spawn_rng.argtypes = [vp, vp, vp, i32, vp]
     L.tc_debug_set_timeline.argtypes = [vp, vp]
     L.tc_noise_blobs.argtypes = [vp, vp, C.c_uint64, C.c_uint32, i32, i32, i32, vp, vp]
     L.tc_reset.argtypes = [vp, vp, vp, C.POINTER(TcOutputs), vp]
@@ -94,7 +95,7 @@ def lib():
     L.tc_profile_begin.argtypes = [vp, i32]
     L.tc_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32)]
     L.tc_debug_layer_query.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double, i32, i32, vp, vp, vp]
-    for name in ("tc_noise_blobs", "tc_step_f64", "tc_debug_set_timeline", "tc_set_autoreset", "tc_create", "tc_destroy", "tc_set_car_params", "tc_set_camera_params", "tc_set_wrapped", "tc_reset", "tc_step",
+    for name in ("tc_set_spawn_rng", "tc_noise_blobs", "tc_step_f64", "tc_debug_set_timeline", "tc_set_autoreset", "tc_create", "tc_destroy", "tc_set_car_params", "tc_set_camera_params", "tc_set_wrapped", "tc_reset", "tc_step",
                  "tc_render", "tc_get_state", "tc_set_state", "tc_step_host", "tc_debug_layer_query", "tc_profile_begin", "tc_profile_end"):
         getattr(L, name).restype = C.c_int
     if L.tc_abi_version() != 1:

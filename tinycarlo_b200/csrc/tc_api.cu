@@ -71,10 +71,11 @@ struct TcHandle {
     int fused_all = 0, fused_nodes = 0, fused_edges = 0, fused_cblob = 0, fused_words = 0;
     TcClassBlob all_desc{};
     int32_t edge_off_h[TC_MAX_CLASSES + 1] = {0};
-    uint8_t *ar_done = nullptr; // autoreset: caller-owned device buffers
-    const int32_t *ar_table = nullptr;
-    int32_t *ar_cursor = nullptr;
-    int ar_k = 0;
+    uint8_t *ar_done = nullptr; // autoreset flags: caller-owned device buffer
+    uint64_t *rng = nullptr;    // spawn streams: caller-owned device buffers
+    const int32_t *spawn_points = nullptr;
+    int n_spawn_points = 0;
+    int32_t *last_spawn = nullptr;
     // optional per-kernel CUDA-event timing (tc_profile_begin/end)
     bool profiling = false;
     int prof_cap = 0, prof_used = 0; // step slots
@@ -283,10 +284,18 @@ int tc_set_camera_params(TcHandle *h, const double *dev_cam, const int32_t *dev_
     return TC_OK;
 }
 
-int tc_set_autoreset(TcHandle *h, uint8_t *dev_done, const int32_t *dev_spawn_table, int32_t table_len, int32_t *dev_cursor) {
+int tc_set_autoreset(TcHandle *h, uint8_t *dev_done) {
     if (!h) return tc_fail(TC_ERR_INVALID, "tc_set_autoreset: null handle");
-    if (dev_done && (!dev_spawn_table || !dev_cursor || table_len <= 0)) return tc_fail(TC_ERR_INVALID, "tc_set_autoreset: incomplete spawn table");
-    h->ar_done = dev_done; h->ar_table = dev_spawn_table; h->ar_cursor = dev_cursor; h->ar_k = dev_done ? table_len : 0;
+    if (dev_done && !h->rng) return tc_fail(TC_ERR_STATE, "tc_set_autoreset: set the spawn streams first (tc_set_spawn_rng)");
+    h->ar_done = dev_done;
+    return TC_OK;
+}
+
+int tc_set_spawn_rng(TcHandle *h, uint64_t *dev_rng_state, const int32_t *dev_spawn_points, int32_t n_spawn_points, int32_t *dev_last_spawn) {
+    if (!h) return tc_fail(TC_ERR_INVALID, "tc_set_spawn_rng: null handle");
+    if (n_spawn_points < 0 || (n_spawn_points > 0 && !dev_spawn_points)) return tc_fail(TC_ERR_INVALID, "tc_set_spawn_rng: bad spawn_points");
+    h->rng = dev_rng_state; h->spawn_points = dev_spawn_points; h->n_spawn_points = n_spawn_points; h->last_spawn = dev_last_spawn;
+    if (!dev_rng_state) h->ar_done = nullptr;
     return TC_OK;
 }
 
@@ -359,7 +368,7 @@ static int tc_launch_track(TcHandle *h, int mode, const float *cc, const int32_t
     ta.blob = h->d_blob; ta.layout = h->layout; ta.n_envs = h->n_envs; ta.mode = mode; ta.wrapped = h->wrapped;
     ta.sf = h->d_sf; ta.si = h->d_si; ta.car = h->d_car; ta.cam = h->d_cam; ta.pose = h->d_pose;
     ta.act_cc = cc; ta.act_cc64 = cc64; ta.act_man = man; ta.mask = mask; ta.spawn_nodes = spawn;
-    ta.done = h->ar_done; ta.spawn_table = h->ar_table; ta.spawn_cursor = h->ar_cursor; ta.spawn_k = h->ar_k;
+    ta.done = h->ar_done; ta.rng = h->rng; ta.spawn_points = h->spawn_points; ta.n_spawn_points = h->n_spawn_points; ta.last_spawn = h->last_spawn;
     if (outs) ta.out = *outs;
     const int envs_per_block = TC_TRACK_THREADS / 32;
     tc_track_kernel<<<(h->n_envs + envs_per_block - 1) / envs_per_block, TC_TRACK_THREADS, h->track_smem, st>>>(ta);
@@ -369,7 +378,8 @@ static int tc_launch_track(TcHandle *h, int mode, const float *cc, const int32_t
 }
 
 int tc_reset(TcHandle *h, const uint8_t *dev_mask, const int32_t *dev_spawn_nodes, const TcOutputs *outs, void *stream) {
-    if (!h || !dev_spawn_nodes) return tc_fail(TC_ERR_INVALID, "tc_reset: null argument");
+    if (!h) return tc_fail(TC_ERR_INVALID, "tc_reset: null handle");
+    if (!dev_spawn_nodes && !h->rng) return tc_fail(TC_ERR_STATE, "tc_reset: no spawn nodes given and no spawn streams set (tc_set_spawn_rng)");
     if (!h->car_set || !h->cam_set) return tc_fail(TC_ERR_STATE, "tc_reset: car/camera parameters not set");
     TC_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;

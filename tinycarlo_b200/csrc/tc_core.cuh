@@ -386,6 +386,67 @@ TC_HD TcInfo tc_get_info(const TcLanes &g, const TcTrackTables &t, const double 
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------ spawn draws
+// map.py:51-69 on the device: numpy's Generator(PCG64(SeedSequence(seed))) stream of every env continues inside the reset
+// path, so resets need no host round trip. State row (uint64 x 5): LCG state hi, lo, increment hi, lo, and the bit
+// generator's buffered 32-bit half (bit 32 = valid, low 32 bits = value). Seeding (SeedSequence hashing, pcg64_srandom)
+// stays on the host (tinycarlo_b200/pcg64.py); the stepping below is numpy's pcg64_next64 / pcg64_next32 /
+// buffered_bounded_lemire_uint32, checked against numpy and against the reference's recorded draws.
+TC_HD uint64_t tc_mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+TC_HD uint64_t tc_pcg_next64(uint64_t *st) {
+    const uint64_t MH = 0x2360ED051FC65DA4ull, ML = 0x4385DF649FCCF645ull;
+    uint64_t hi = st[TC_RNG_HI], lo = st[TC_RNG_LO];
+    uint64_t plo = lo * ML;
+    uint64_t phi = tc_mulhi64(lo, ML) + lo * MH + hi * ML;
+    uint64_t nlo = plo + st[TC_RNG_INC_LO];
+    uint64_t nhi = phi + st[TC_RNG_INC_HI] + (nlo < plo ? 1u : 0u);
+    st[TC_RNG_HI] = nhi; st[TC_RNG_LO] = nlo;
+    unsigned rot = (unsigned)(nhi >> 58);
+    uint64_t x = nhi ^ nlo;
+    return (x >> rot) | (x << ((64 - rot) & 63));
+}
+TC_HD uint32_t tc_pcg_next32(uint64_t *st) {
+    if (st[TC_RNG_BUF] >> 32) {
+        uint32_t v = (uint32_t)st[TC_RNG_BUF];
+        st[TC_RNG_BUF] = 0;
+        return v;
+    }
+    uint64_t v = tc_pcg_next64(st);
+    st[TC_RNG_BUF] = (1ull << 32) | (v >> 32);
+    return (uint32_t)v;
+}
+// Generator.integers(0, n) / the index of Generator.choice(seq of length n), n < 2^32
+TC_HD uint32_t tc_pcg_bounded(uint64_t *st, uint32_t n) {
+    if (n <= 1) return 0;
+    const uint32_t rng = n - 1;
+    if (rng == 0xFFFFFFFFu) return tc_pcg_next32(st);
+    const uint64_t rng_excl = (uint64_t)rng + 1;
+    uint64_t m = (uint64_t)tc_pcg_next32(st) * rng_excl;
+    uint32_t leftover = (uint32_t)m;
+    if (leftover < rng_excl) {
+        const uint32_t threshold = (uint32_t)((0xFFFFFFFFu - rng) % rng_excl);
+        while (leftover < threshold) {
+            m = (uint64_t)tc_pcg_next32(st) * rng_excl;
+            leftover = (uint32_t)m;
+        }
+    }
+    return (uint32_t)(m >> 32);
+}
+// one spawn node: choice(spawn_points) or integers(0, n_nodes-1), redrawn while the node has no successor (map.py:61-64)
+TC_HD int tc_spawn_draw(const TcTrackTables &t, uint64_t *st, const int32_t *choices, int n_choices) {
+    for (int guard = 0; guard < 100000; guard++) {
+        int node = n_choices > 0 ? choices[tc_pcg_bounded(st, (uint32_t)n_choices)] : (int)tc_pcg_bounded(st, (uint32_t)(t.lp_n_nodes - 1));
+        if (node >= 0 && node < t.lp_n_nodes && t.next_off[node] != t.next_off[node + 1]) return node;
+    }
+    return -1;
+}
+
 // ------------------------------------------------------------------------------------------------ camera.py
 // numpy matmul == OpenBLAS dgemm on these shapes: c_ij = fma(a_i3,b_3j, fma(a_i2,b_2j, fma(a_i1,b_1j, a_i0*b_0j)))
 TC_HD void tc_mm_chain(const double *A, int ar, int ac, const double *B, int bc, double *C) {

@@ -166,3 +166,15 @@ HT_API void ht_polyline(uint8_t *img, int H, int W, int32_t x0, int32_t y0, int3
     for (size_t p = 0; p < (size_t)(y_hi - y_lo) * W; p++)
         if ((plane[p >> 5] >> (p & 31)) & 1) img[(size_t)y_lo * W + p] = 255;
 }
+
+// the reset paths' spawn draws (tc_spawn_draw): k consecutive draws of n env streams, states advanced in place
+HT_API void ht_spawn_draws(const HtMap *m, int n, uint64_t *rng_state, const int32_t *spawn_points, int n_spawn_points, int k, int32_t *out) {
+    TcTrackTables t = tc_track_tables(m->pk.blob.data(), m->pk.L);
+    for (int env = 0; env < n; env++)
+        for (int j = 0; j < k; j++) out[(size_t)env * k + j] = tc_spawn_draw(t, rng_state + (size_t)env * TC_RNG_N, spawn_points, n_spawn_points);
+}
+// Generator.integers(0, high_excl) on n streams (tc_pcg_bounded), k draws each
+HT_API void ht_pcg_bounded(int n, uint64_t *rng_state, uint32_t high_excl, int k, uint32_t *out) {
+    for (int env = 0; env < n; env++)
+        for (int j = 0; j < k; j++) out[(size_t)env * k + j] = tc_pcg_bounded(rng_state + (size_t)env * TC_RNG_N, high_excl);
+}

@@ -67,9 +67,11 @@ struct TcTrackArgs {
     const int32_t *spawn_nodes; // reset
     // next-step autoreset (gymnasium AutoresetMode.NEXT_STEP): an env whose previous step ended is reset by this step
     uint8_t *done;              // [N] in/out, NULL = autoreset off
-    const int32_t *spawn_table; // [N, spawn_k] pre-drawn spawn nodes
-    int32_t *spawn_cursor;      // [N]
-    int spawn_k;
+    // spawn draws on the device (tc_set_spawn_rng): per-env PCG64 state, optional spawn_points list, last node drawn
+    uint64_t *rng;              // [N, TC_RNG_N]
+    const int32_t *spawn_points;
+    int n_spawn_points;
+    int32_t *last_spawn;        // [N] out: lanepath node of the env's most recent reset
     TcOutputs out;
 };
 
@@ -100,17 +102,25 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS, 3) tc_track_kernel(const TcT
     bool auto_reset = false;
     if (a.mode == 0 && a.done && a.done[env]) {
         // the action of this step is ignored; reward 0, not terminated, not truncated, empty info (env.py:101-113)
-        int cur = a.spawn_cursor[env];
-        int node = a.spawn_table[(size_t)env * a.spawn_k + (cur < a.spawn_k ? cur : a.spawn_k - 1)];
+        int node = -1;
+        if (g.lane == 0 && a.rng) node = tc_spawn_draw(t, a.rng + (size_t)env * TC_RNG_N, a.spawn_points, a.n_spawn_points);
+        node = __shfl_sync(0xffffffffu, node, 0);
         tc_load_state(sf, si, s);
         auto_reset = tc_car_reset(t, cp, s, node);
-        if (auto_reset && g.lane == 0) a.spawn_cursor[env] = cur + 1;
+        if (auto_reset && g.lane == 0 && a.last_spawn) a.last_spawn[env] = node;
     }
     if (auto_reset) {
     } else if (a.mode == 1) {
         if (a.mask && !a.mask[env]) return;
         tc_load_state(sf, si, s);
-        if (!tc_car_reset(t, cp, s, a.spawn_nodes[env])) return;
+        int node = -1;
+        if (a.spawn_nodes) node = a.spawn_nodes[env];
+        else {
+            if (g.lane == 0 && a.rng) node = tc_spawn_draw(t, a.rng + (size_t)env * TC_RNG_N, a.spawn_points, a.n_spawn_points);
+            node = __shfl_sync(0xffffffffu, node, 0);
+        }
+        if (!tc_car_reset(t, cp, s, node)) return;
+        if (g.lane == 0 && a.last_spawn) a.last_spawn[env] = node;
     } else {
         tc_load_state(sf, si, s);
         // env.py:118: np.clip(action["car_control"], -1, 1) on float64

@@ -166,9 +166,8 @@ class TinyCarloEnv(gc.Env):
         super().reset(seed=seed)
         self._sync_flags()
         node = self.map.sample_spawn_node(self.np_random)   # map.py:51-69 on the env's own generator
-        self._vec._seeded = True
-        if self._vec._spawn_table is None:
-            self._vec._seed(0)   # allocates the (unused) spawn table so that masked resets keep working
+        if not self._vec._seeded:
+            self._vec._seed(0)   # the single env draws on the host generator gymnasium seeded; the device stream stays unused
         self._vec.reset(spawn_nodes=torch.tensor([node], dtype=torch.int32))
         return self._obs(), self._info()
 

@@ -164,6 +164,17 @@ class VecPCG64:
                 first = False
         return res[m]
 
+    # ---- device layout (include/tinycarlo_b200.h TC_RNG_*)
+    def device_rows(self) -> np.ndarray:
+        buf = np.where(self.has32, (_U64(1) << _U64(32)) | self.buf32.astype(_U64), _U64(0))
+        return np.ascontiguousarray(np.stack([self.hi, self.lo, self.inc_hi, self.inc_lo, buf], axis=1).astype(_U64))
+
+    def load_device_rows(self, rows: np.ndarray):
+        r = np.asarray(rows).view(_U64).reshape(-1, 5)
+        self.hi, self.lo, self.inc_hi, self.inc_lo = (r[:, k].copy() for k in range(4))
+        self.has32 = (r[:, 4] >> _U64(32)) != 0
+        self.buf32 = (r[:, 4] & _M32).astype(_U32)
+
     # ---- checkpointing
     def state_dict(self):
         return {k: getattr(self, k).copy() for k in ("hi", "lo", "inc_hi", "inc_lo", "has32", "buf32")}

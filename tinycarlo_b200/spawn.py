@@ -2,10 +2,12 @@
 
 gymnasium's Env.reset(seed=s) installs np.random.Generator(PCG64(SeedSequence(s))); each reset then makes one bounded
 draw (choice(spawn_points), or integers(0, n_nodes-1) without spawn points) and redraws while the node has no
-successor. The sequence of spawn nodes of an env therefore depends only on (seed, number of resets), so the host
-pre-draws K resets ahead per env into a table that the device consumes with a per-env cursor.
-Env i of a vectorised env is seeded with seed + global_index(i), like gymnasium.vector. The per-env streams are
-evaluated on numpy arrays by tinycarlo_b200/pcg64.py (bit-compatible with numpy's Generator, ~1 us per 20 draws)."""
+successor. Env i of a vectorised env is seeded with seed + global_index(i), like gymnasium.vector.
+
+The product draws on the DEVICE: spawn_stream_states() seeds one PCG64 stream per env on the host (SeedSequence hashing,
+tinycarlo_b200/pcg64.py) and the reset paths of the tracking kernel advance it (tc_spawn_draw in csrc/tc_core.cuh), so
+resets never synchronise with the host. SpawnSampler is the host model of the same streams on numpy arrays: it tells
+what the device must draw (tests, tools) and is not on the step path."""
 from typing import Optional
 
 import numpy as np
@@ -16,6 +18,18 @@ from .pcg64 import VecPCG64
 
 def make_generator(seed: Optional[int]) -> np.random.Generator:
     return np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+
+
+def stream_seeds(num_envs: int, seed: Optional[int], env_index_offset: int = 0) -> np.ndarray:
+    if seed is None:   # OS entropy, one independent stream per env
+        return np.random.SeedSequence().generate_state(int(num_envs), np.uint64)
+    return np.arange(int(num_envs), dtype=np.uint64) + np.uint64(int(seed) + int(env_index_offset))
+
+
+def spawn_stream_states(num_envs: int, seed: Optional[int], env_index_offset: int = 0) -> np.ndarray:
+    """uint64 [num_envs, 5] in the layout of include/tinycarlo_b200.h TC_RNG_*: the freshly seeded
+    Generator(PCG64(SeedSequence(seed + offset + i))) of every env (state hi, lo, increment hi, lo, empty 32-bit buffer)."""
+    return VecPCG64(stream_seeds(num_envs, seed, env_index_offset)).device_rows()
 
 
 class SpawnSampler:
@@ -43,11 +57,7 @@ class SpawnSampler:
         return out[m]
 
     def seed(self, seed: Optional[int]):
-        if seed is None:   # OS entropy, one independent stream per env
-            seeds = np.random.SeedSequence().generate_state(self.n, np.uint64)
-        else:
-            seeds = np.arange(self.n, dtype=np.uint64) + np.uint64(int(seed) + self.offset)
-        self.rng = VecPCG64(seeds)
+        self.rng = VecPCG64(stream_seeds(self.n, seed, self.offset))
         tab = np.empty((self.n, self.K), np.int32)
         all_envs = np.ones(self.n, bool)
         for k in range(self.K):

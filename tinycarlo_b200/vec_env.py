@@ -18,7 +18,7 @@ from . import _lib
 from .camera_params import camera_row
 from .config import camera_params, car_param_row, load_config, resolve_map_path, sim_params
 from .maptables import MapTables
-from .spawn import SpawnSampler
+from .spawn import spawn_stream_states
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -29,8 +29,8 @@ class TinyCarloVecEnv:
     is_vector_env = True
 
     def __init__(self, config: Union[str, Dict[str, Any]], num_envs: int, device: Union[str, int, torch.device] = "cuda",
-                 obs_format: Optional[str] = None, env_index_offset: int = 0, spawn_table_len: Optional[int] = None,
-                 debug_segments: bool = False, autoreset: Optional[str] = None):
+                 obs_format: Optional[str] = None, env_index_offset: int = 0, debug_segments: bool = False,
+                 autoreset: Optional[str] = None):
         """config: yaml path / directory / dict as for the reference env. num_envs: envs on THIS device.
         env_index_offset: global index of local env 0 (multi-GPU sharding: env i is seeded with seed + offset + i, so
         results do not depend on how the envs are sharded). debug_segments: also export the projected int32 segments.
@@ -97,7 +97,7 @@ class TinyCarloVecEnv:
             if debug_segments:
                 self.out["seg_count"] = torch.zeros((N, Cn), dtype=torch.int32, device=dev)
                 self.out["seg_i32"] = torch.zeros((N, max(int(m.ll_edge_off[-1]), 1), 4), dtype=torch.int32, device=dev)
-            self._spawn_nodes = torch.zeros(N, dtype=torch.int32, device=dev)
+            self._spawn_nodes = torch.full((N,), -1, dtype=torch.int32, device=dev)   # node of each env's latest reset
             self._mask_all = torch.ones(N, dtype=torch.uint8, device=dev)
         self._outs = self._make_outputs(with_obs=True)
         self._outs_noobs = self._make_outputs(with_obs=False)
@@ -109,15 +109,21 @@ class TinyCarloVecEnv:
         self._thickness = np.full(N, int(cc["line_thickness"]), np.int32)
         self._upload_params()
 
-        # ---- spawn draws (map.py:51-69): per-env numpy Generators seeded like gymnasium, pre-drawn K resets ahead
+        # ---- spawn draws (map.py:51-69) on the device: one numpy-compatible PCG64 stream per env, seeded like gymnasium
+        # (Generator(PCG64(SeedSequence(seed + global index)))) on the host and advanced inside the reset paths of the
+        # tracking kernel, so resets and autoresets never synchronise with the host.
         if autoreset not in (None, "next_step"):
             raise ValueError("autoreset must be None or 'next_step'")
         self.autoreset = autoreset
-        self._K = int(spawn_table_len) if spawn_table_len else (64 if autoreset else 16)
-        self._sampler = SpawnSampler(self.map, N, self._K, self.env_index_offset)
-        self._spawn_table = None   # device int32 [N, K]
-        self._spawn_cursor = None  # device int32 [N]
-        self._resets_since_refill = 0
+        with torch.cuda.device(dev):
+            self._rng_state = torch.zeros((N, _lib.TC_RNG_N), dtype=torch.int64, device=dev)   # uint64 bit patterns
+            sp = self.map.spawn_points
+            self._spawn_points = None if sp is None else torch.tensor(sp, dtype=torch.int32, device=dev)
+            self.done_flags = torch.zeros(N, dtype=torch.uint8, device=dev) if autoreset else None
+        _lib.check(self._L.tc_set_spawn_rng(self._h, _ptr(self._rng_state), _ptr(self._spawn_points), 0 if sp is None else len(sp),
+                                            _ptr(self._spawn_nodes)), "tc_set_spawn_rng")
+        if autoreset:
+            _lib.check(self._L.tc_set_autoreset(self._h, _ptr(self.done_flags)), "tc_set_autoreset")
         self._seeded = False
 
     # ------------------------------------------------------------------------------------------------ plumbing
@@ -217,30 +223,10 @@ class TinyCarloVecEnv:
 
     # ------------------------------------------------------------------------------------------------ spawn draws
     def _seed(self, seed: Optional[int]):
-        tab = self._sampler.seed(seed)
-        self._upload_spawn_table(tab)
-        self._seeded = True
-
-    def _upload_spawn_table(self, tab: np.ndarray):
+        st = spawn_stream_states(self.num_envs, seed, self.env_index_offset)
         with torch.cuda.device(self.device):
-            if self._spawn_table is None:
-                self._spawn_table = torch.from_numpy(tab).to(self.device)
-                self._spawn_cursor = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
-                if self.autoreset:
-                    # buffers registered with the library must keep their addresses: refills copy in place
-                    self.done_flags = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
-                    _lib.check(self._L.tc_set_autoreset(self._h, _ptr(self.done_flags), _ptr(self._spawn_table), self._K,
-                                                        _ptr(self._spawn_cursor)), "tc_set_autoreset")
-            else:
-                self._spawn_table.copy_(torch.from_numpy(tab))
-                self._spawn_cursor.zero_()
-        self._resets_since_refill = 0
-
-    def _refill_spawn_table_if_due(self):
-        """Each reset()/autoreset step consumes at most one pre-drawn spawn node per env; after K of them the cursors are
-        read back (the only host sync of the env, every K calls) and the consumed entries are replaced by fresh draws."""
-        if self._resets_since_refill >= self._K - 1:
-            self._upload_spawn_table(self._sampler.advance(self._spawn_cursor.cpu().numpy()))
+            self._rng_state.copy_(torch.from_numpy(st.view(np.int64)))   # in place: the library holds the address
+        self._seeded = True
 
     # ------------------------------------------------------------------------------------------------ gym-like API
     def _info(self) -> Dict[str, torch.Tensor]:
@@ -260,20 +246,9 @@ class TinyCarloVecEnv:
                 mask_u8 = mask.to(device=self.device, dtype=torch.uint8).contiguous()
             else:
                 mask_u8 = self._mask_all
+            nodes = None   # NULL: every selected env draws from its own device stream
             if spawn_nodes is not None:
                 nodes = spawn_nodes.to(device=self.device, dtype=torch.int32).contiguous()
-            else:
-                self._refill_spawn_table_if_due()
-                cur = self._spawn_cursor.long().clamp_(max=self._K - 1)
-                nodes = torch.gather(self._spawn_table, 1, cur[:, None])[:, 0].contiguous()
-                if mask is None and not int(self._resets_since_refill):
-                    # a full reset right after (re)seeding consumed exactly one entry per env: top the table up now,
-                    # without reading the cursors back, so that the first refill does not land in somebody's timed loop
-                    self._upload_spawn_table(self._sampler.advance(np.ones(self.num_envs, np.int64)))
-                else:
-                    self._spawn_cursor += mask_u8.to(torch.int32)
-                    self._resets_since_refill += 1
-            self._spawn_nodes = nodes
             if self.autoreset:
                 self.done_flags.masked_fill_(mask_u8.bool(), 0)
             outs = self._outs if not self.no_observation else self._outs_noobs
@@ -294,11 +269,8 @@ class TinyCarloVecEnv:
             raise ValueError("action tensors must live on the env's device with shapes [N,2] and [N]")
         outs = self._outs if not self.no_observation else self._outs_noobs
         with torch.cuda.device(self.device):
-            if self.autoreset:
-                if not self._seeded:
-                    raise _lib.TinyCarloError("call reset() before step()")
-                self._refill_spawn_table_if_due()
-                self._resets_since_refill += 1
+            if self.autoreset and not self._seeded:
+                raise _lib.TinyCarloError("call reset() before step()")
             fn = self._L.tc_step_f64 if f64 else self._L.tc_step
             _lib.check(fn(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
         o = self.out
@@ -320,9 +292,6 @@ class TinyCarloVecEnv:
         back, and the stream synchronised inside the call (tc_step_host). Observations stay on the device in self.obs."""
         outs = self._outs if not self.no_observation else self._outs_noobs
         with torch.cuda.device(self.device):
-            if self.autoreset:
-                self._refill_spawn_table_if_due()
-                self._resets_since_refill += 1
             _lib.check(self._L.tc_step_host(self._h, _ptr(car_control), _ptr(maneuver), C.byref(outs), _ptr(reward), _ptr(terminated),
                                             _ptr(truncated), _ptr(cte), _ptr(heading_error), self._stream()), "tc_step_host")
 
@@ -353,25 +322,22 @@ class TinyCarloVecEnv:
         return {"sf": sf, "si": si}
 
     def checkpoint(self) -> Dict[str, Any]:
-        """Everything needed to resume a rollout bit for bit: car state, the spawn streams (per-env PCG64 states, the
-        pre-drawn table and its cursors) and the autoreset flags. The reference has no counterpart."""
+        """Everything needed to resume a rollout bit for bit: car state, the spawn streams (per-env PCG64 states) and the
+        autoreset flags. The reference has no counterpart."""
         ck = {k: v.cpu() for k, v in self.state_dict().items()}
         if self._seeded:
-            ck["spawn_cursor"] = self._spawn_cursor.cpu()
-            ck["spawn_sampler"] = self._sampler.state_dict()
-            ck["resets_since_refill"] = self._resets_since_refill
-        if self.autoreset and hasattr(self, "done_flags"):
+            ck["spawn_rng"] = self._rng_state.cpu()
+            ck["last_spawn"] = self._spawn_nodes.cpu()
+        if self.autoreset:
             ck["done_flags"] = self.done_flags.cpu()
         return ck
 
     def restore(self, ck: Dict[str, Any]):
         self.load_state_dict({"sf": ck["sf"], "si": ck["si"]})
-        if "spawn_sampler" in ck:
-            self._sampler.load_state_dict(ck["spawn_sampler"])
+        if "spawn_rng" in ck:
+            self._rng_state.copy_(ck["spawn_rng"])
+            self._spawn_nodes.copy_(ck["last_spawn"])
             self._seeded = True
-            self._upload_spawn_table(self._sampler.table)
-            self._spawn_cursor.copy_(ck["spawn_cursor"])
-            self._resets_since_refill = int(ck["resets_since_refill"])
         if "done_flags" in ck and self.autoreset:
             self.done_flags.copy_(ck["done_flags"])
         self.render_obs()

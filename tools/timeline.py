@@ -14,7 +14,7 @@ from tinycarlo_b200 import TinyCarloVecEnv
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 cfg = make_config("knuffingen", "classes", cam={"resolution": [480, 640]})
-env = TinyCarloVecEnv(cfg, N, device="cuda:0", autoreset="next_step", spawn_table_len=4)
+env = TinyCarloVecEnv(cfg, N, device="cuda:0", autoreset="next_step")
 env.reset(seed=0)
 cc = torch.zeros((N, 2), device="cuda"); cc[:, 0] = 0.8
 man = torch.zeros(N, dtype=torch.int32, device="cuda")
