@@ -172,6 +172,13 @@ TC_API int tc_profile_end(TcHandle *h, double *host_ms_sum /*[3]*/, int32_t *hos
  * shared memory, camera pass done, rasterisation done, stores issued, segment count, cycles zeroing / set-up / drawing. NULL switches it off. (tools/timeline.py) */
 TC_API int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline);
 
+/* Debug hook: the visible-set tables of the block-per-env render kernel (small frames; tinycarlo_b200/csrc/tc_cull.h).
+ * host_out4 = camera reach R in metres the tables were built for (-1: culling off, the whole laneline graph is processed;
+ * -2: this handle renders per class and has no such tables), number of cell descriptors, mean and maximum node count of a
+ * cell. tc_set_camera_params rebuilds the tables (and synchronises the stream) when the cameras' reach changes. Setting
+ * the environment variable TC_CULL=0 switches the culling off. */
+TC_API int tc_debug_cull_info(TcHandle *h, double *host_out4);
+
 /* Test hook: the reference's Layer queries (layer.py) evaluated by the DEVICE functions on class 0 of the handle's map.
  * op: 0 get_nearest_edge(pos) 1 get_nearest_edge_with_orientation(pos, a) 2 is_position_within_edge_bounds(pos, e=(i0,i1))
  *     3 distance_to_edge(pos, e) 4 clip_angle(a).  Results: out_i[0], out_d[0] (device pointers). */

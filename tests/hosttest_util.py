@@ -14,7 +14,7 @@ SRC = os.path.join(_lib.CSRC, "tc_hosttest.cpp")
 
 
 def build():
-    deps = [SRC] + [os.path.join(_lib.CSRC, f) for f in ("tc_core.cuh", "tc_pack.h")]
+    deps = [SRC] + [os.path.join(_lib.CSRC, f) for f in ("tc_core.cuh", "tc_pack.h", "tc_cull.h")]
     if not os.path.exists(HT_PATH) or os.path.getmtime(HT_PATH) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(_lib.LIB_DIR, exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fvisibility=hidden", "-shared", "-x", "c++",
@@ -37,6 +37,13 @@ def ht():
         L.ht_render.argtypes = [vp, i, i, i, i, i] + [vp] * 7
         L.ht_spawn_draws.argtypes = [vp, i, vp, vp, i, i, vp]
         L.ht_pcg_bounded.argtypes = [i, vp, C.c_uint32, i, vp]
+        L.ht_cull_create.restype = vp
+        L.ht_cull_create.argtypes = [C.POINTER(_lib.TcMapDesc), C.c_double, C.c_double, C.c_double]
+        L.ht_cull_destroy.argtypes = [vp]
+        L.ht_cull_info.argtypes = [vp, vp]
+        L.ht_cull_radius_of.restype = C.c_double
+        L.ht_cull_radius_of.argtypes = [vp, i, i]
+        L.ht_project_culled.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp]
         L.ht_polyline.argtypes = [vp, i, i, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i, i, i, i]
         _ht = L
     return _ht
@@ -56,6 +63,7 @@ class HostCore:
         k = self.keep
         desc = _lib.TcMapDesc(m.n_classes, P(k[0]), P(k[1]), P(k[2]), P(k[3]), P(k[4]), len(m.lp_nodes), len(m.lp_edges), P(k[5]),
                               P(k[6]), P(k[7]), P(k[8]))
+        self.desc = desc
         self.h = ht().ht_map_create(C.byref(desc))
         assert self.h
         self.n, self.H, self.W, self.C = n, H, W, m.n_classes
@@ -84,6 +92,19 @@ class HostCore:
     def render(self, mask=None):
         ht().ht_render(self.h, self.n, self.H, self.W, self.fmt, self.rows_per_band, P(self.pose), P(self.cam), P(self.thick), P(mask),
                        P(self.obs), P(self.seg_count), P(self.seg))
+
+    def project_culled(self, radius, cell=0.25, margin=0.05):
+        """segments of the current poses through the visible-set tables built for camera reach `radius` ->
+        (seg_count [n,C], seg [n,sumE,4], nodes of each env's cell, table info)"""
+        hc = ht().ht_cull_create(C.byref(self.desc), float(radius), float(cell), float(margin))
+        cnt = np.zeros_like(self.seg_count)
+        seg = np.zeros_like(self.seg)
+        cell_nodes = np.zeros(self.n, np.int32)
+        info = np.zeros(6)
+        ht().ht_project_culled(self.h, hc, self.n, self.H, self.W, P(self.pose), P(self.cam), P(cnt), P(seg), P(cell_nodes))
+        ht().ht_cull_info(hc, P(info))
+        ht().ht_cull_destroy(hc)
+        return cnt, seg, cell_nodes, info
 
     def reset(self, spawn_nodes, mask=None, render=True):
         sp = np.ascontiguousarray(spawn_nodes, np.int32)

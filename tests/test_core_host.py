@@ -8,12 +8,24 @@ import numpy as np
 import pytest
 
 from golden_util import SCENARIOS, Golden
-from hosttest_util import HostCore, polyline
+from hosttest_util import HostCore, P, ht, polyline
 from tinycarlo_b200.camera_params import camera_row
 from tinycarlo_b200.config import car_param_row, resolve_map_path
 from tinycarlo_b200.maptables import MapTables
 
 cv2 = pytest.importorskip("cv2")
+
+
+def same_segments(tables, cnt_a, seg_a, cnt_b, seg_b):
+    """per class, the first count entries (the arrays keep stale rows behind them)"""
+    if not np.array_equal(cnt_a, cnt_b):
+        return False
+    for c in range(tables.n_classes):
+        o = int(tables.ll_edge_off[c])
+        for i in np.nonzero(cnt_a[:, c])[0]:
+            if not np.array_equal(seg_a[i, o:o + cnt_a[i, c]], seg_b[i, o:o + cnt_a[i, c]]):
+                return False
+    return True
 
 
 def cam_row_from(E, K, mr):
@@ -34,6 +46,7 @@ def test_host_core_replays_reference_trace(name):
     env = HostCore(tables, 1, car_param_row(cfg["car"], 1 / cfg["sim"].get("fps", 30)), row0, cc["line_thickness"], g.H, g.W, g.fmt,
                    wrapped=g.wrapped, rows_per_band=32 if g.H > 64 else 0)
     mr = g.max_range_per_frame()
+    radius_of = {}
     for f in range(g.F):
         env.cam[0] = cam_row_from(g["E"][f], g["K"][f], mr[f])
         if g["ev_kind"][f] == 0:
@@ -64,6 +77,14 @@ def test_host_core_replays_reference_trace(name):
             assert np.array_equal(env.obs[0], g.classes_frame(f)), (name, f)
         else:
             assert hashlib.sha256(env.obs[0].tobytes()).hexdigest().encode() == g["rgb_sha"][f], (name, f)
+        # the visible-set tables of the block-per-env kernel give the reference's segments too (tables per camera row,
+        # as tc_set_camera_params rebuilds them)
+        if f % 5 == 0 or g["ev_kind"][f] == 0:
+            key = env.cam[0].tobytes()
+            if key not in radius_of:
+                radius_of[key] = ht().ht_cull_radius_of(P(env.cam[0]), g.H, g.W)
+            cnt, seg, cell_nodes, info = env.project_culled(radius_of[key])
+            assert same_segments(tables, cnt, seg, env.seg_count, env.seg), (name, f, "culled camera pass")
 
 
 @pytest.mark.parametrize("H,W,spread,n,nlanes", [(24, 32, 12, 4000, 1), (24, 32, 12, 3000, 32), (24, 32, 12, 3000, -1), (48, 64, 300, 2500, -1),
@@ -154,3 +175,68 @@ def test_device_spawn_streams_equal_numpy_and_reference_draws():
         spp = None if sp is None else np.asarray(sp, np.int32)
         ht().ht_spawn_draws(core.h, 40, P(st), P(spp), 0 if sp is None else len(sp), 12, P(out))
         assert np.array_equal(out, want[13:53]), key
+
+
+def _poses(E, xy, rot):
+    """camera.py:61 with car.py:159-165 in plain numpy (both camera passes under test take the same pose)"""
+    n = len(rot)
+    c, s_ = np.cos(-rot), np.sin(-rot)
+    M = np.zeros((n, 4, 4))
+    M[:, 0, 0], M[:, 0, 1], M[:, 1, 0], M[:, 1, 1], M[:, 2, 2], M[:, 3, 3] = c, -s_, s_, c, 1, 1
+    T = np.tile(np.eye(4), (n, 1, 1))
+    T[:, 0, 3], T[:, 1, 3] = -xy[:, 0], -xy[:, 1]
+    return np.ascontiguousarray((E[None] @ (M @ T)).reshape(n, 12))
+
+
+@pytest.mark.parametrize("map_name,ppm,res,cam", [
+    ("knuffingen", 222, [128, 160], {}), ("knuffingen", 222, [480, 640], {"max_range": 1.5}), ("knuffingen", 222, [84, 84], {"fov": 125, "orientation": [10, 0, 0]}),
+    ("knuffingen", 222, [128, 160], {"max_range": 0.2, "position": [0.02, -0.01, 0.02], "orientation": [35, 4, -6]}),
+    ("simple_layout", 450, [84, 84], {}), ("simple_layout", 450, [84, 84], {"max_range": 0.15}),
+    ("formula_student_track", 100, [128, 160], {"max_range": 3.0}), ("formula_student_skidpad", 100, [96, 128], {"max_range": 1.0})])
+def test_visible_set_tables_never_change_the_segments(map_name, ppm, res, cam):
+    """tc_cull.h: the camera pass on the sub-graph of the camera's ground cell emits exactly the segments of the pass over the
+    whole map - for cameras on the track, next to it, on cell borders, far outside the map, at any yaw."""
+    from pair_util import make_config
+    from tinycarlo_b200.config import camera_params
+    cfg = make_config(map_name, "classes", cam=dict({"resolution": res}, **cam), spawn=None)
+    ppm = cfg["map"]["pixel_per_meter"]
+    tables = MapTables(resolve_map_path(cfg["map"], None), ppm, None)
+    cc = camera_params(cfg["camera"])
+    row = camera_row(cc["position"], cc["orientation"], cc["fov"], cc["resolution"], cc["max_range"])
+    H, W = res
+    rng = np.random.default_rng(len(map_name) + H)
+    nodes = np.asarray(tables.ll_nodes, np.float64).reshape(-1, 2)
+    lo, hi = nodes.min(0), nodes.max(0)
+    n = 6000
+    near = nodes[rng.integers(0, len(nodes), n // 2)] + rng.normal(0, 0.15, (n // 2, 2))      # on / next to the lines
+    anywhere = rng.uniform(lo - 1.5, hi + 1.5, (n // 4, 2))
+    on_nodes = nodes[rng.integers(0, len(nodes), n - n // 2 - n // 4)]                          # degenerate: camera base on a node
+    xy = np.concatenate([near, anywhere, on_nodes])
+    rot = rng.uniform(-np.pi, np.pi, n)
+    rot[::7] = np.round(rot[::7] / (np.pi / 2)) * (np.pi / 2)                                    # axis-aligned views: edges parallel to the clip planes
+    env = HostCore(tables, n, np.zeros(8), row, 2, H, W)
+    env.pose[:] = _poses(row[:12].reshape(3, 4), xy, rot)
+    env.obs = None
+    env.render()
+    radius = ht().ht_cull_radius_of(P(row), H, W)
+    assert radius > 0
+    for cell in (0.25, 0.1):
+        cnt, seg, cell_nodes, info = env.project_culled(radius, cell=cell)
+        assert same_segments(tables, cnt, seg, env.seg_count, env.seg), (map_name, cell)
+    assert env.seg_count.sum() > n, "the poses should see something"
+    if info[0] > 0:   # culling active: the sub-graphs are smaller than the map
+        assert info[3] <= 0.85 * len(nodes) and cell_nodes.max() <= info[3]
+
+
+def test_cull_radius_rejects_cameras_outside_the_argument():
+    cc = {"position": [0, -0.005, 0.04], "orientation": [22, 0, 0], "fov": 80, "resolution": [128, 160], "max_range": 0.5}
+    row = camera_row(cc["position"], cc["orientation"], cc["fov"], cc["resolution"], cc["max_range"])
+    r = ht().ht_cull_radius_of(P(row), 128, 160)
+    fx, fy, cx, cy = row[12:16]
+    assert abs(r - 0.5 * np.sqrt(1 + (max(cx, 160 - cx) / fx) ** 2 + (max(cy, 128 - cy) / fy) ** 2)) < 1e-12
+    bad = row.copy(); bad[1] *= 1.01                                   # extrinsics no longer a rotation
+    assert ht().ht_cull_radius_of(P(bad), 128, 160) < 0
+    ground = camera_row([0, 0, 0.0], cc["orientation"], 80, [128, 160], 0.5)   # camera in the ground plane
+    assert ht().ht_cull_radius_of(P(ground), 128, 160) < 0
+    inf = row.copy(); inf[16] = np.inf
+    assert ht().ht_cull_radius_of(P(inf), 128, 160) < 0

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "tc_kernels.cuh"
+#include "tc_cull.h"
 #include "tc_pack.h"
 
 // Kernel attributes are per function, not per handle: several handles with different shared-memory needs coexist
@@ -71,6 +72,15 @@ struct TcHandle {
     int fused_all = 0, fused_nodes = 0, fused_edges = 0, fused_cblob = 0, fused_words = 0;
     TcClassBlob all_desc{};
     int32_t edge_off_h[TC_MAX_CLASSES + 1] = {0};
+    // block-per-env kernel: visible-set tables (tc_cull.h), rebuilt when the camera parameters change
+    std::vector<int32_t> m_node_off, m_edge_off, m_edges; // host copy of the laneline tables (the builder's input)
+    std::vector<double> m_nodes;
+    TcCellBlob *d_cell_desc = nullptr;
+    unsigned char *d_cell_blob = nullptr;
+    TcCullGrid cull_grid{};
+    int env_np = 0, env_max_bytes = 0, env_words = 0;
+    double cull_radius = -1.0, cull_mean_nodes = 0.0;
+    int cull_cells = 0, cull_max_nodes = 0;
     uint8_t *ar_done = nullptr; // autoreset flags: caller-owned device buffer
     uint64_t *rng = nullptr;    // spawn streams: caller-owned device buffers
     const int32_t *spawn_points = nullptr;
@@ -114,6 +124,39 @@ static void tc_band_geometry(int H, int W, int planes, size_t smem_budget, int *
     *plane_words = words(rows);
 }
 
+static TcMapDesc tc_host_map(const TcHandle *h) {
+    TcMapDesc m{};
+    m.n_classes = h->C; m.ll_node_off = h->m_node_off.data(); m.ll_edge_off = h->m_edge_off.data();
+    m.ll_nodes = h->m_nodes.data(); m.ll_edges = h->m_edges.data();
+    return m;
+}
+// (re)builds the visible-set tables for camera reach `radius` (< 0: culling off) and moves them to the device
+static int tc_install_cull(TcHandle *h, double radius) {
+    TcCull cull;
+    TcMapDesc m = tc_host_map(h);
+    double cell = 0.25;
+    if (const char *cs = getenv("TC_CULL_CELL")) cell = atof(cs) > 0 ? atof(cs) : cell;
+    if (const char *ce = getenv("TC_CULL")) if (atoi(ce) == 0) radius = -1.0;
+    tc_build_cull(&m, radius, cell, 0.05, cull);
+    const size_t np = tc_env_np(cull.max_nodes, cull.max_edges);
+    const size_t smem = tc_env_smem_bytes(np, cull.max_bytes, h->env_words);
+    if (smem > 200 * 1024) return tc_fail(TC_ERR_INVALID, "visible-set tables exceed the shared-memory budget");
+    TcCellBlob *dd = nullptr;
+    unsigned char *db = nullptr;
+    TC_CUDA(cudaMalloc((void **)&dd, cull.desc.size() * sizeof(TcCellBlob)));
+    cudaError_t e = cudaMalloc((void **)&db, std::max<size_t>(cull.blob.size(), 16));
+    if (e != cudaSuccess) { cudaFree(dd); return tc_fail(TC_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    TC_CUDA(cudaDeviceSynchronize());   // kernels that still read the old tables
+    TC_CUDA(cudaMemcpy(dd, cull.desc.data(), cull.desc.size() * sizeof(TcCellBlob), cudaMemcpyHostToDevice));
+    if (!cull.blob.empty()) TC_CUDA(cudaMemcpy(db, cull.blob.data(), cull.blob.size(), cudaMemcpyHostToDevice));
+    cudaFree(h->d_cell_desc);
+    cudaFree(h->d_cell_blob);
+    h->d_cell_desc = dd; h->d_cell_blob = db;
+    h->cull_grid = cull.grid; h->env_np = (int)np; h->env_max_bytes = cull.max_bytes; h->render_smem = smem;
+    h->cull_radius = cull.radius; h->cull_mean_nodes = cull.mean_nodes; h->cull_cells = (int)cull.desc.size(); h->cull_max_nodes = cull.max_nodes;
+    return TC_OK;
+}
+
 extern "C" {
 
 int tc_abi_version(void) { return TC_ABI_VERSION; }
@@ -123,6 +166,8 @@ int tc_destroy(TcHandle *h) {
     if (!h) return TC_OK;
     cudaSetDevice(h->device);
     for (void *p : h->allocs) cudaFree(p);
+    cudaFree(h->d_cell_desc);
+    cudaFree(h->d_cell_blob);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     delete h;
     return TC_OK;
@@ -150,6 +195,10 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     h->device = device; h->n_envs = num_envs; h->C = C; h->H = sim->height; h->W = sim->width; h->obs_format = sim->obs_format;
     h->sum_nodes = sumN; h->sum_edges = sumE;
     memcpy(h->colors, map->ll_colors, (size_t)3 * C);
+    h->m_node_off.assign(map->ll_node_off, map->ll_node_off + C + 1);
+    h->m_edge_off.assign(map->ll_edge_off, map->ll_edge_off + C + 1);
+    h->m_nodes.assign(map->ll_nodes, map->ll_nodes + 2 * (size_t)sumN);
+    h->m_edges.assign(map->ll_edges, map->ll_edges + 2 * (size_t)sumE);
     h->max_nodes = pk.max_nodes;
     h->layout = pk.L;
     const TcBlobLayout &L = h->layout;
@@ -233,28 +282,34 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
         // one block per (env, class) with a full-frame plane, or - when all C planes, the union graph and its scratch fit
         // comfortably (small frames) - one block per env rendering all classes: 1/C of the blocks, barriers and table loads
         const int words_all = (int)(((size_t)C * h->H * h->W + 31) / 32) + 1;
-        const size_t smem_all = tc_render_smem_bytes(sumN, sumE, pk.all_desc.bytes, words_all);
+        TcCull whole;
+        tc_build_cull(map, -1.0, 0.25, 0.05, whole);
+        const size_t smem_all = tc_env_smem_bytes(tc_env_np(whole.max_nodes, whole.max_edges), whole.max_bytes, words_all);
         const size_t smem_one = tc_render_smem_bytes(h->max_nodes, h->max_edges, h->max_cblob_bytes, h->plane_words_full);
         bool all = smem_all <= 100 * 1024 && (size_t)C * h->H * h->W <= 128 * 1024;
         if (const char *fa = getenv("TC_FUSED_ALL")) all = atoi(fa) != 0 && smem_all <= 200 * 1024;
         h->fused_all = all ? 1 : 0;
-        h->fused_nodes = all ? sumN : h->max_nodes; h->fused_edges = all ? sumE : h->max_edges;
-        h->fused_cblob = all ? pk.all_desc.bytes : h->max_cblob_bytes; h->fused_words = all ? words_all : h->plane_words_full;
-        h->render_smem = all ? smem_all : smem_one;
+        h->fused_nodes = h->max_nodes; h->fused_edges = h->max_edges;
+        h->fused_cblob = h->max_cblob_bytes; h->fused_words = h->plane_words_full;
+        h->render_smem = smem_one;
+        h->env_words = words_all;
         h->fused_ok = all || smem_one <= 56 * 1024; // >= 4 blocks per SM; larger frames take the banded two-kernel path
+        if (all) TC_TRYH(tc_install_cull(h, -1.0));   // the whole graph until the camera parameters are known
     }
     if (h->fused_ok) {
         if (const char *rt = getenv("TC_RENDER_THREADS")) h->render_threads = atoi(rt) == 128 ? 128 : 256;
-        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<128, TC_FMT_U8>));
-        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, TC_FMT_BITS>));
-        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, TC_FMT_BF16>));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, TC_FMT_BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, TC_FMT_BF16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<128, TC_FMT_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, TC_FMT_U8>));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, TC_FMT_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDAH(tc_allow_max_smem(tc_render_classes_kernel<256, TC_FMT_RGB>));
-        TC_CUDAH(cudaFuncSetAttribute(tc_render_classes_kernel<256, TC_FMT_RGB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#define TC_PREP_RENDER(K)                 \
+    TC_CUDAH(tc_allow_max_smem(K));       \
+    TC_CUDAH(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+        TC_PREP_RENDER((tc_render_env_kernel<128, TC_FMT_U8>));
+        TC_PREP_RENDER((tc_render_env_kernel<256, TC_FMT_U8>));
+        TC_PREP_RENDER((tc_render_env_kernel<256, TC_FMT_RGB>));
+        TC_PREP_RENDER((tc_render_env_kernel<256, TC_FMT_BITS>));
+        TC_PREP_RENDER((tc_render_env_kernel<256, TC_FMT_BF16>));
+        TC_PREP_RENDER((tc_render_classes_kernel<256, TC_FMT_U8>));
+        TC_PREP_RENDER((tc_render_classes_kernel<256, TC_FMT_BITS>));
+        TC_PREP_RENDER((tc_render_classes_kernel<256, TC_FMT_BF16>));
+#undef TC_PREP_RENDER
     }
     TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -281,6 +336,18 @@ int tc_set_camera_params(TcHandle *h, const double *dev_cam, const int32_t *dev_
     TC_CUDA(cudaMemcpyAsync(h->d_cam, dev_cam, (size_t)h->n_envs * TC_CAM_N * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     TC_CUDA(cudaMemcpyAsync(h->d_thick, dev_thickness, (size_t)h->n_envs * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     h->cam_set = true;
+    if (h->fused_all) {
+        // the visible-set tables depend on how far the cameras see: read the rows back (this call synchronises) and rebuild
+        std::vector<double> rows((size_t)h->n_envs * TC_CAM_N);
+        TC_CUDA(cudaMemcpyAsync(rows.data(), h->d_cam, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        TC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        double radius = 0.0;
+        for (int i = 0; i < h->n_envs && radius >= 0; i++) {
+            double r = tc_cull_radius_of(rows.data() + (size_t)i * TC_CAM_N, h->H, h->W);
+            radius = r < 0 ? -1.0 : std::max(radius, r);
+        }
+        if (radius != h->cull_radius && !(radius >= 0 && h->cull_radius >= radius && h->cull_radius <= 1.05 * radius)) TC_TRY(tc_install_cull(h, radius));
+    }
     return TC_OK;
 }
 
@@ -313,24 +380,41 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
         if (obs_format == TC_OBS_CLASSES_BF16 && (h->H * h->W) % 8 != 0) return tc_fail(TC_ERR_INVALID, "bf16 observations need H*W to be a multiple of 8");
         if (obs_format == TC_OBS_CLASSES_BITS && h->fused_all && (h->H * h->W) % 32 != 0) return tc_fail(TC_ERR_INVALID, "bit-packed observations of small frames need H*W to be a multiple of 32");
     }
-    if (obs && h->fused_ok && !seg_count_out && !seg_out && (obs_format != TC_OBS_RGB || h->fused_all)) {
+    if (obs && h->fused_ok && h->fused_all && !seg_count_out && !seg_out) {
+        TcRenderEnvArgs ea;
+        ea.cell_desc = h->d_cell_desc; ea.cell_blob = h->d_cell_blob; ea.grid = h->cull_grid; ea.n_envs = N; ea.n_classes = C;
+        ea.np = h->env_np; ea.max_bytes = h->env_max_bytes; ea.H = h->H; ea.W = h->W; ea.plane_words = h->env_words;
+        ea.pose = h->d_pose; ea.cam = h->d_cam; ea.thickness = h->d_thick; ea.mask = mask; ea.obs = obs;
+        memcpy(ea.colors, h->colors, sizeof(ea.colors));
+        ea.timeline = mask ? nullptr : h->timeline;
+        if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
+        const size_t sm = h->render_smem;
+        if (obs_format == TC_OBS_RGB) tc_render_env_kernel<256, TC_FMT_RGB><<<N, 256, sm, st>>>(ea);
+        else if (obs_format == TC_OBS_CLASSES_BITS) tc_render_env_kernel<256, TC_FMT_BITS><<<N, 256, sm, st>>>(ea);
+        else if (obs_format == TC_OBS_CLASSES_BF16) tc_render_env_kernel<256, TC_FMT_BF16><<<N, 256, sm, st>>>(ea);
+        else if (h->render_threads == 128) tc_render_env_kernel<128, TC_FMT_U8><<<N, 128, sm, st>>>(ea);
+        else tc_render_env_kernel<256, TC_FMT_U8><<<N, 256, sm, st>>>(ea);
+        h->launches++;
+        TC_CUDA(cudaGetLastError());
+        return TC_OK;
+    }
+    if (obs && h->fused_ok && !seg_count_out && !seg_out && obs_format != TC_OBS_RGB) {
         TcRenderArgs fa;
         fa.cblob_desc = h->d_cblob_desc; fa.cblob = h->d_cblob; fa.max_cblob_bytes = h->fused_cblob; fa.n_envs = N; fa.n_classes = C;
         fa.max_nodes = h->fused_nodes; fa.max_edges = h->fused_edges;
-        fa.H = h->H; fa.W = h->W; fa.plane_words = h->fused_words; fa.all_classes = h->fused_all; fa.all_desc = h->all_desc;
+        fa.H = h->H; fa.W = h->W; fa.plane_words = h->fused_words; fa.all_classes = 0; fa.all_desc = h->all_desc;
         memcpy(fa.edge_off, h->edge_off_h, sizeof(fa.edge_off));
-        fa.rgb = obs_format == TC_OBS_RGB ? 1 : 0;
+        fa.rgb = 0;
         memcpy(fa.colors, h->colors, sizeof(fa.colors)); fa.pose = h->d_pose; fa.cam = h->d_cam; fa.thickness = h->d_thick;
         fa.mask = mask; fa.obs = obs;
         fa.stagger_ns = mask ? 0 : h->stagger_ns; fa.n_sms = h->n_sms;
         fa.timeline = mask ? nullptr : h->timeline;
         if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
-        const int grid = h->fused_all ? N : N * C;
-        if (obs_format == TC_OBS_RGB) tc_render_classes_kernel<256, TC_FMT_RGB><<<grid, 256, h->render_smem, st>>>(fa);
-        else if (obs_format == TC_OBS_CLASSES_BITS) tc_render_classes_kernel<256, TC_FMT_BITS><<<grid, 256, h->render_smem, st>>>(fa);
-        else if (obs_format == TC_OBS_CLASSES_BF16) tc_render_classes_kernel<256, TC_FMT_BF16><<<grid, 256, h->render_smem, st>>>(fa);
-        else if (h->render_threads == 128) tc_render_classes_kernel<128, TC_FMT_U8><<<grid, 128, h->render_smem, st>>>(fa);
-        else tc_render_classes_kernel<256, TC_FMT_U8><<<grid, 256, h->render_smem, st>>>(fa);
+        const int grid = N * C;
+        const size_t sm = h->render_smem;
+        if (obs_format == TC_OBS_CLASSES_BITS) tc_render_classes_kernel<256, TC_FMT_BITS><<<grid, 256, sm, st>>>(fa);
+        else if (obs_format == TC_OBS_CLASSES_BF16) tc_render_classes_kernel<256, TC_FMT_BF16><<<grid, 256, sm, st>>>(fa);
+        else tc_render_classes_kernel<256, TC_FMT_U8><<<grid, 256, sm, st>>>(fa);
         h->launches++;
         TC_CUDA(cudaGetLastError());
         return TC_OK;
@@ -488,6 +572,12 @@ int tc_step_host(TcHandle *h, const float *host_car_control, const int32_t *host
 int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline) {
     if (!h) return tc_fail(TC_ERR_INVALID, "tc_debug_set_timeline: null handle");
     h->timeline = dev_timeline;
+    return TC_OK;
+}
+
+int tc_debug_cull_info(TcHandle *h, double *out4) {
+    if (!h || !out4) return tc_fail(TC_ERR_INVALID, "tc_debug_cull_info: null argument");
+    out4[0] = h->fused_all ? h->cull_radius : -2.0; out4[1] = h->cull_cells; out4[2] = h->cull_mean_nodes; out4[3] = h->cull_max_nodes;
     return TC_OK;
 }
 

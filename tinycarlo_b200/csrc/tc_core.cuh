@@ -529,6 +529,39 @@ TC_HD TcClassTables tc_class_tables_from_blob(const unsigned char *base, const T
     return ct;
 }
 
+// Visible-set tables of the block-per-env render kernel (built by tc_cull.h, which also states why the result is unchanged):
+// the sub-graph of the union of all classes that a camera standing in one ground cell can see. Same sections as a class
+// blob plus a per-node "core" byte (only core nodes may be visible) and a per-edge class byte.
+struct TcCellBlob {
+    int32_t n_nodes, n_edges;
+    int32_t offset, bytes; // inside the cell-blob buffer; bytes is a multiple of 16 (0: empty cell)
+    int32_t off_edges, off_out_off, off_out_edge, off_in_off, off_in_edge, off_core, off_edge_cls;
+};
+struct TcCullGrid {
+    double x0, y0, inv_cell;
+    int32_t nx, ny; // nx == 0: culling off, descriptor 0 is the whole graph; descriptor nx*ny is the empty one (outside the grid)
+};
+// descriptor index for a camera whose world->camera pose is the row-major 3x4 [R|t]: the camera centre is -R^T t
+TC_HD int tc_cull_cell(const TcCullGrid &g, const double *pose) {
+    if (g.nx == 0) return 0;
+    double cx = -(pose[0] * pose[3] + pose[4] * pose[7] + pose[8] * pose[11]);
+    double cy = -(pose[1] * pose[3] + pose[5] * pose[7] + pose[9] * pose[11]);
+    double fx = floor((cx - g.x0) * g.inv_cell), fy = floor((cy - g.y0) * g.inv_cell);
+    if (!(fx >= 0 && fx < g.nx && fy >= 0 && fy < g.ny)) return g.nx * g.ny; // also NaN poses: nothing is visible
+    return (int)fy * g.nx + (int)fx;
+}
+TC_HD TcClassTables tc_class_tables_from_cell(const unsigned char *base, const TcCellBlob &b) {
+    TcClassTables ct;
+    ct.n_nodes = b.n_nodes; ct.n_edges = b.n_edges;
+    ct.nodes = (const double *)base;
+    ct.edges = (const int32_t *)(base + b.off_edges);
+    ct.out_off = (const int32_t *)(base + b.off_out_off);
+    ct.out_edge = (const int32_t *)(base + b.off_out_edge);
+    ct.in_off = (const int32_t *)(base + b.off_in_off);
+    ct.in_edge = (const int32_t *)(base + b.off_in_edge);
+    return ct;
+}
+
 // Scratch of one camera pass (shared memory on the device).
 struct TcProjScratch {
     double *Px, *Py, *Pz; // [n]

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "tc_core.cuh"
+#include "tc_cull.h"
 #include "tc_pack.h"
 
 #define HT_API extern "C" __attribute__((visibility("default")))
@@ -177,4 +178,63 @@ HT_API void ht_spawn_draws(const HtMap *m, int n, uint64_t *rng_state, const int
 HT_API void ht_pcg_bounded(int n, uint64_t *rng_state, uint32_t high_excl, int k, uint32_t *out) {
     for (int env = 0; env < n; env++)
         for (int j = 0; j < k; j++) out[(size_t)env * k + j] = tc_pcg_bounded(rng_state + (size_t)env * TC_RNG_N, high_excl);
+}
+
+// ---- visible-set tables (tc_cull.h): the camera pass of tc_render_env_kernel on the sub-graph of the camera's ground cell
+struct HtCull { TcCull c; };
+HT_API HtCull *ht_cull_create(const TcMapDesc *map, double radius, double cell, double margin) {
+    HtCull *h = new HtCull();
+    tc_build_cull(map, radius, cell, margin, h->c);
+    return h;
+}
+HT_API void ht_cull_destroy(HtCull *h) { delete h; }
+HT_API void ht_cull_info(const HtCull *h, double *out6) {
+    out6[0] = h->c.radius; out6[1] = (double)h->c.desc.size(); out6[2] = h->c.mean_nodes; out6[3] = h->c.max_nodes;
+    out6[4] = h->c.grid.nx; out6[5] = h->c.grid.ny;
+}
+HT_API double ht_cull_radius_of(const double *cam_row, int H, int W) { return tc_cull_radius_of(cam_row, H, W); }
+
+// mirrors the geometry phase of tc_render_env_kernel; output in the layout of ht_render's segment arrays (per class, list order)
+HT_API void ht_project_culled(const HtMap *m, const HtCull *hc, int n, int H, int W, const double *pose, const double *cam, int32_t *seg_count,
+                              int32_t *seg, int32_t *cell_nodes /* optional [n] */) {
+    const int C = m->C;
+    for (int env = 0; env < n; env++) {
+        const double *ps = pose + (size_t)env * 12, *cm = cam + (size_t)env * TC_CAM_N;
+        const TcCellBlob d = hc->c.desc[tc_cull_cell(hc->c.grid, ps)];
+        if (cell_nodes) cell_nodes[env] = d.n_nodes;
+        for (int c = 0; c < C; c++) seg_count[(size_t)env * C + c] = 0;
+        if (d.n_nodes == 0) continue;
+        const unsigned char *base = hc->c.blob.data() + d.offset;
+        const TcClassTables ct = tc_class_tables_from_cell(base, d);
+        const uint8_t *core = base + d.off_core, *edge_cls = base + d.off_edge_cls;
+        const int nn = d.n_nodes, mm = d.n_edges;
+        std::vector<double> Px(nn + 1), Py(nn + 1), Pz(nn + 1);
+        std::vector<int32_t> ix(nn + 1), iy(nn + 1);
+        std::vector<uint8_t> fA(nn + 1), fB(nn + 1), rA(nn + 1), rB(nn + 1), vis(nn + 1);
+        TcProjScratch sc = {Px.data(), Py.data(), Pz.data(), ix.data(), iy.data(), fA.data(), rA.data(), vis.data()};
+        const double max_range = cm[TC_CAM_MAX_RANGE];
+        for (int v = 0; v < nn; v++) {
+            tc_transform_node(ps, ct.nodes[2 * v], ct.nodes[2 * v + 1], Px[v], Py[v], Pz[v]);
+            fA[v] = Pz[v] < 0;
+        }
+        for (int v = 0; v < nn; v++) fB[v] = fA[v] | (uint8_t)tc_clip_pass_node(ct, sc, fA.data(), v, true, -0.0000001);
+        for (int v = 0; v < nn; v++) fA[v] = fB[v] | (uint8_t)tc_clip_pass_node(ct, sc, fB.data(), v, false, -0.0000001);
+        for (int v = 0; v < nn; v++) rA[v] = Pz[v] > -max_range;
+        for (int v = 0; v < nn; v++) rB[v] = rA[v] | (uint8_t)tc_clip_pass_node(ct, sc, rA.data(), v, true, -max_range);
+        for (int v = 0; v < nn; v++) rA[v] = rB[v] | (uint8_t)tc_clip_pass_node(ct, sc, rB.data(), v, false, -max_range);
+        for (int v = 0; v < nn; v++) {
+            double u, w;
+            tc_project(cm, Px[v], Py[v], Pz[v], u, w);
+            ix[v] = tc_np_int32(u);
+            iy[v] = tc_np_int32(w);
+            vis[v] = (core[v] && u > 0 && u < W && w > 0 && w < H && fA[v] && rA[v]) ? 1 : 0;
+        }
+        for (int e = 0; e < mm; e++) {
+            int n0 = ct.edges[2 * e], n1 = ct.edges[2 * e + 1];
+            if (!(vis[n0] || vis[n1])) continue;
+            const int c = edge_cls[e];
+            int32_t *s = seg + ((size_t)env * m->sumE + m->edge_off[c] + seg_count[(size_t)env * C + c]++) * 4;
+            s[0] = ix[n0]; s[1] = iy[n0]; s[2] = ix[n1]; s[3] = iy[n1];
+        }
+    }
 }

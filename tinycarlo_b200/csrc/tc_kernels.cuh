@@ -735,6 +735,223 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const 
 #undef TC_TL
 }
 
+// ------------------------------------------------------------------------------------------------ fused, block per env
+// Small frames: a block renders ALL classes of an env into one stacked C*H-row plane (1/C of the barriers, table loads and
+// launches of the per-class kernel). A separate kernel from tc_render_classes_kernel because its time goes elsewhere - into
+// the camera pass and the rasteriser's set-up, not into the stores - and so that the headline kernel's register allocation
+// (64 registers, no spills) is not disturbed. What it does differently:
+//  * the camera pass runs on the sub-graph of the ground cell the camera stands in (TcCellBlob, tc_cull.h) instead of the
+//    whole map: 3-7x fewer nodes on Knuffingen, and a third of the shared memory (more blocks per SM);
+//  * set-up takes 32 segments per round (lane = segment, warp = role) and every primitive is then drawn by ONE thread - the
+//    segments of a small frame are a few pixels long, a warp-wide draw keeps 5 lanes busy; a primitive with more than
+//    TC_SMALL_PRIM_ITEMS items is handed to the whole warp on the spot;
+//  * shared memory is reused aggressively: the segment list overlays the camera-frame coordinates once they are projected,
+//    plane and primitive slots overlay the projected coordinates, flags and tables.
+#define TC_SMALL_PRIM_ITEMS 48
+#define TC_ENV_CHUNK 32
+#define TC_ENV_SEG_WORDS (TC_MAX_PRIMS_PER_SEG * 8 + 1) // 12 slots of 8 words, padded: lanes reading one slot of 32 segments hit 32 banks
+__device__ __forceinline__ int tc_prim_items(const TcPrim &q) {
+    if (q.kind == TC_PRIM_LINE2) return q.a[4] + 1;
+    if (q.kind == TC_PRIM_SPAN) return q.a[2] - q.a[1];
+    if (q.kind == TC_PRIM_CIRCLE) return 4 * (q.a[2] + 1);
+    if (q.kind == TC_PRIM_BRES) return q.a[4] + 1;
+    return 0;
+}
+
+struct TcRenderEnvArgs {
+    const TcCellBlob *cell_desc;   // device
+    const unsigned char *cell_blob;
+    TcCullGrid grid;
+    int n_envs, n_classes;
+    int np;                    // node capacity of the scratch arrays (multiple of 16; >= every cell's node count, 24*np >= 17*max edges)
+    int max_bytes;             // largest cell blob
+    int H, W;
+    int plane_words;           // words of the stacked C*H-row bit plane (incl. pad word)
+    const double *pose;        // [N,12]
+    const double *cam;         // [N,TC_CAM_N]
+    const int32_t *thickness;  // [N]
+    const uint8_t *mask;       // optional
+    uint8_t *obs;
+    uint8_t colors[TC_MAX_CLASSES * 3];
+    long long *timeline;       // optional debug [N][10], see tools/timeline.py
+};
+// shared memory: phase 1 [Px Py Pz | ix iy | 5 flag arrays | cell tables (TMA)]; phase 2 [segments + classes | plane | primitive slots]
+__host__ __device__ inline size_t tc_env_np(int max_nodes, int max_edges) {
+    size_t need = ((size_t)17 * (max_edges > 0 ? max_edges : 1) + 23) / 24;   // 16 B segment + 1 B class per edge inside 24*np bytes
+    size_t np = (size_t)max_nodes > need ? (size_t)max_nodes : need;
+    return (np + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t tc_env_off_tables(size_t np) { return (np * 37 + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t tc_env_off_plane(size_t np) { return np * 24; }
+__host__ __device__ inline size_t tc_env_off_prims(size_t np, int plane_words) { return (np * 24 + (size_t)plane_words * 4 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t tc_env_smem_bytes(size_t np, int max_bytes, int plane_words) {
+    size_t a = tc_env_off_tables(np) + (size_t)max_bytes;
+    size_t b = tc_env_off_prims(np, plane_words) + (((size_t)TC_ENV_CHUNK * TC_ENV_SEG_WORDS * 4 + 15) & ~(size_t)15);
+    return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
+
+template <int NT, int FMT>
+__global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRenderEnvArgs a) {
+    constexpr bool RGB = FMT == TC_FMT_RGB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int seg_cnt;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double s_pose[12], s_cam[TC_CAM_N];
+    __shared__ uint32_t s_color24[TC_MAX_CLASSES];
+    __shared__ TcCellBlob s_desc;
+    const int env = blockIdx.x;
+    if (a.mask && !a.mask[env]) return;
+    const int tid = threadIdx.x;
+#ifdef TC_TIMELINE
+#define TC_TL(stmt) do { if (a.timeline && tid == 0) { stmt; } } while (0)
+    long long tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0, tl_setup = 0, tl_draw = 0, tl_z = 0, tc0 = 0;
+#else
+#define TC_TL(stmt) do { } while (0)
+#endif
+    TC_TL(tl0 = clock64());
+    const size_t np = (size_t)a.np;
+    unsigned char *tab_smem = smem_raw + tc_env_off_tables(np);
+    if (tid == 0) {
+        // which part of the map can this camera see: its ground cell selects the tables (one TMA bulk copy)
+        const TcCellBlob d = a.cell_desc[tc_cull_cell(a.grid, a.pose + (size_t)env * 12)];
+        seg_cnt = 0;
+        tc_mbar_init(&bar, 1);
+        tc_fence_mbar_init();
+        if (d.bytes > 0) {
+            tc_mbar_expect_tx(&bar, (uint32_t)d.bytes);
+            tc_bulk_g2s(tab_smem, a.cell_blob + d.offset, (uint32_t)d.bytes, &bar);
+        }
+        s_desc = d;
+    }
+    if (RGB && tid >= 64 && tid < 64 + TC_MAX_CLASSES) {
+        const int cc = tid - 64;
+        s_color24[cc] = a.colors[3 * cc] | (a.colors[3 * cc + 1] << 8) | (a.colors[3 * cc + 2] << 16);
+    }
+    if (tid >= 32 && tid < 44) s_pose[tid - 32] = a.pose[(size_t)env * 12 + tid - 32];
+    else if (tid >= 44 && tid < 44 + (TC_CAM_MAX_RANGE - TC_CAM_FX + 1)) s_cam[TC_CAM_FX + tid - 44] = a.cam[(size_t)env * TC_CAM_N + TC_CAM_FX + tid - 44];
+    __syncthreads();      // barrier init, descriptor, pose and intrinsics visible to all threads
+    const int n = s_desc.n_nodes, m = s_desc.n_edges;
+    int4 *segs = (int4 *)smem_raw;                                   // phase 2 views
+    uint32_t *plane = (uint32_t *)(smem_raw + tc_env_off_plane(np));
+    int32_t *pw = (int32_t *)(smem_raw + tc_env_off_prims(np, a.plane_words));
+    if (n > 0) {
+        TcProjScratch sc;
+        sc.Px = (double *)smem_raw; sc.Py = sc.Px + np; sc.Pz = sc.Py + np;
+        sc.ix = (int32_t *)(sc.Pz + np); sc.iy = sc.ix + np;
+        uint8_t *fA = (uint8_t *)(sc.iy + np), *fB = fA + np, *rA = fB + np, *rB = rA + np;
+        sc.vis = rB + np; sc.front = fA; sc.inr = rA;
+        const double *pose = s_pose, *cam = s_cam;
+        const double max_range = cam[TC_CAM_MAX_RANGE];
+        tc_mbar_wait(&bar, 0); // the cell's tables have landed in shared memory
+        TC_TL(tl1 = clock64());
+        const TcClassTables ct = tc_class_tables_from_cell(tab_smem, s_desc);
+        const uint8_t *core = tab_smem + s_desc.off_core, *edge_cls = tab_smem + s_desc.off_edge_cls;
+        for (int v = tid; v < n; v += NT) {
+            double X, Y, Z;
+            tc_transform_node(pose, ct.nodes[2 * v], ct.nodes[2 * v + 1], X, Y, Z);
+            sc.Px[v] = X; sc.Py[v] = Y; sc.Pz[v] = Z;
+            fA[v] = Z < 0;
+        }
+        __syncthreads();
+        for (int v = tid; v < n; v += NT) fB[v] = fA[v] | (uint8_t)tc_clip_pass_node(ct, sc, fA, v, true, -0.0000001);
+        __syncthreads();
+        for (int v = tid; v < n; v += NT) fA[v] = fB[v] | (uint8_t)tc_clip_pass_node(ct, sc, fB, v, false, -0.0000001);
+        __syncthreads();
+        for (int v = tid; v < n; v += NT) rA[v] = sc.Pz[v] > -max_range;
+        __syncthreads();
+        for (int v = tid; v < n; v += NT) rB[v] = rA[v] | (uint8_t)tc_clip_pass_node(ct, sc, rA, v, true, -max_range);
+        __syncthreads();
+        for (int v = tid; v < n; v += NT) rA[v] = rB[v] | (uint8_t)tc_clip_pass_node(ct, sc, rB, v, false, -max_range);
+        __syncthreads();
+        for (int v = tid; v < n; v += NT) {
+            double u, w;
+            tc_project(cam, sc.Px[v], sc.Py[v], sc.Pz[v], u, w);
+            sc.ix[v] = tc_np_int32(u);
+            sc.iy[v] = tc_np_int32(w);
+            sc.vis[v] = (core[v] && u > 0 && u < a.W && w > 0 && w < a.H && fA[v] && rA[v]) ? 1 : 0;
+        }
+        __syncthreads();   // the camera-frame coordinates are dead: the segment list takes their place
+        uint8_t *seg_cls = (uint8_t *)(segs + m);
+        // kept edges (camera.py:95); order is irrelevant for single-colour planes, and in RGB the classes keep their order
+        for (int e = tid; e < m; e += NT) {
+            int n0 = ct.edges[2 * e], n1 = ct.edges[2 * e + 1];
+            if (sc.vis[n0] || sc.vis[n1]) {
+                int slot = atomicAdd(&seg_cnt, 1);
+                segs[slot] = make_int4(sc.ix[n0], sc.iy[n0], sc.ix[n1], sc.iy[n1]);
+                seg_cls[slot] = edge_cls[e];
+            }
+        }
+        __syncthreads();   // projected coordinates, flags and tables are dead: plane and primitive slots take their place
+    }
+    const int cnt = seg_cnt;
+    TC_TL(tl2 = clock64());
+    const int n_planes = a.n_classes;
+    if (cnt > 0) {
+        const uint8_t *seg_cls = (const uint8_t *)(segs + m);
+        for (int i = tid; i < a.plane_words; i += NT) plane[i] = 0;
+        __syncthreads();
+        TC_TL(tl_z = clock64());
+        const int t = a.thickness[env];
+        const int warp = tid >> 5, lane = tid & 31;
+        const TcLanes g = {lane, 32}, g1 = {0, 1};
+        for (int base = 0; base < cnt; base += TC_ENV_CHUNK) {
+            const int nseg = min(TC_ENV_CHUNK, cnt - base);
+            TC_TL(tc0 = clock64());
+            for (int i = tid; i < nseg * TC_MAX_PRIMS_PER_SEG; i += NT)
+                pw[(i / TC_MAX_PRIMS_PER_SEG) * TC_ENV_SEG_WORDS + (i % TC_MAX_PRIMS_PER_SEG) * 8] = TC_PRIM_NONE;
+            __syncthreads();
+            if (lane < nseg) {
+                int4 s4 = segs[base + lane];
+                for (int role = warp; role < TC_N_ROLES; role += NT / 32)
+                    tc_polyline_setup(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, role, (TcPrim *)(pw + lane * TC_ENV_SEG_WORDS));
+            }
+            __syncthreads();
+            TC_TL(long long x = clock64(); tl_setup += x - tc0; tc0 = x);
+            // one thread per primitive; a warp takes one slot (= one kind of primitive) of the 32 segments
+            for (int p = tid; p < TC_MAX_PRIMS_PER_SEG * 32; p += NT) {   // uniform trip count within a warp
+                const int slot = p >> 5;
+                const TcPrim *q = (const TcPrim *)(pw + lane * TC_ENV_SEG_WORDS + slot * 8);
+                int items = 0;
+                if (lane < nseg && q->kind != TC_PRIM_NONE) items = tc_prim_items(*q);
+                if (items > 0 && items <= TC_SMALL_PRIM_ITEMS) {
+                    TcPlane pl = {plane, a.H, a.W, 0, a.H, -(int)seg_cls[base + lane] * a.H};
+                    tc_prim_draw(g1, pl, *q);
+                }
+                unsigned big = __ballot_sync(0xffffffffu, items > TC_SMALL_PRIM_ITEMS);
+                while (big) {   // the few long ones: the whole warp draws them
+                    const int src = __ffs(big) - 1;
+                    big &= big - 1;
+                    const TcPrim *qq = (const TcPrim *)(pw + src * TC_ENV_SEG_WORDS + slot * 8);
+                    TcPlane pl = {plane, a.H, a.W, 0, a.H, -(int)seg_cls[base + src] * a.H};
+                    tc_prim_draw(g, pl, *qq);
+                }
+            }
+            __syncthreads();
+            TC_TL(tl_draw += clock64() - tc0);
+        }
+    }
+    TC_TL(tl3 = clock64());
+    if (FMT == TC_FMT_RGB)
+        tc_store_rgb<NT>(a.obs + (size_t)env * a.H * a.W * 3, (uint32_t)(a.H * a.W), plane, (uint32_t)(a.H * a.W), a.n_classes, s_color24, cnt > 0);
+    else if (FMT == TC_FMT_BITS) {
+        // planes are whole words here (the host only selects this format for H*W % 32 == 0)
+        const int words = (int)(((size_t)a.H * a.W + 31) / 32) * n_planes;
+        tc_store_bits<NT>((uint32_t *)a.obs + (size_t)env * words, words, plane, cnt > 0);
+    } else if (FMT == TC_FMT_BF16)
+        tc_store_bf16<NT>((uint16_t *)a.obs + (size_t)env * n_planes * a.H * a.W, (uint32_t)(n_planes * a.H * a.W), plane, cnt > 0);
+    else tc_store_plane<NT>(a.obs + (size_t)env * n_planes * a.H * a.W, (size_t)n_planes * a.H * a.W, plane, cnt > 0);
+#ifdef TC_TIMELINE
+    if (a.timeline && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *r = a.timeline + (size_t)blockIdx.x * 10;
+        r[0] = smid; r[1] = tl0; r[2] = tl1 ? tl1 : tl0; r[3] = tl2; r[4] = tl3; r[5] = clock64();
+        r[6] = cnt; r[7] = tl_z ? tl_z - tl2 : 0; r[8] = tl_setup; r[9] = tl_draw;
+    }
+#endif
+#undef TC_TL
+}
+
 // ------------------------------------------------------------------------------------------------ blob noise
 // NoiseObservationWrapper (tinycarlo/wrapper/observation.py:14-27) on the device: per class, n_blobs filled circles that
 // either erase the class mask or OR in the pixels of a randomly chosen class, applied in the reference's order (classes

@@ -359,6 +359,13 @@ class TinyCarloVecEnv:
         _lib.check(self._L.tc_profile_end(self._h, ms, C.byref(n)), "tc_profile_end")
         return {"track": ms[0], "project": ms[1], "raster": ms[2]}, int(n.value)
 
+    def cull_info(self) -> Dict[str, float]:
+        """Visible-set tables of the small-frame render kernel (tc_debug_cull_info): camera reach they were built for
+        (-1: culling off, -2: per-class rendering without such tables), cell count, mean / max nodes per cell."""
+        out = (C.c_double * 4)()
+        _lib.check(self._L.tc_debug_cull_info(self._h, out), "tc_debug_cull_info")
+        return {"radius": out[0], "cells": int(out[1]), "mean_nodes": out[2], "max_nodes": int(out[3])}
+
     @property
     def launch_count(self) -> int:
         return int(self._L.tc_launch_count(self._h))

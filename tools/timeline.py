@@ -12,8 +12,12 @@ subprocess.check_call(["nvcc"] + _lib.NVCC_FLAGS + ["-DTC_TIMELINE", "-o", VARIA
 _lib.LIB_PATH = VARIANT
 from tinycarlo_b200 import TinyCarloVecEnv
 
+# usage: timeline.py [N] [map] [H] [W]
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-cfg = make_config("knuffingen", "classes", cam={"resolution": [480, 640]})
+MAP = sys.argv[2] if len(sys.argv) > 2 else "knuffingen"
+RES = [int(sys.argv[3]), int(sys.argv[4])] if len(sys.argv) > 4 else [480, 640]
+cfg = make_config(MAP, "classes", cam={"resolution": RES})
+print(f"--- {MAP} {RES} N={N}")
 env = TinyCarloVecEnv(cfg, N, device="cuda:0", autoreset="next_step")
 env.reset(seed=0)
 cc = torch.zeros((N, 2), device="cuda"); cc[:, 0] = 0.8
@@ -26,6 +30,7 @@ env.step({"car_control": cc, "maneuver": man})
 torch.cuda.synchronize()
 _lib.check(env._L.tc_debug_set_timeline(env._h, None), "timeline")
 t = tl.cpu().numpy()
+t = t[t[:, 5] != 0]   # small frames: one block per env (all classes), the other rows stay empty
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 np.save(os.path.join(ROOT, "gpurun_out", "timeline.npy"), t)
 d = np.diff(t[:, 1:6], axis=1)
