@@ -741,6 +741,7 @@ enum { TC_ROLE_SPANS = 0, TC_ROLE_EDGE0 = 1 /* ..4 */, TC_ROLE_CAPS = 5, TC_N_RO
 // queues behind the observation stores in the load/store pipeline)
 TC_HD int64_t tc_sel4(int i, int64_t a, int64_t b, int64_t c, int64_t d) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : d)); }
 
+template <bool COMPACT>
 TC_HD void tc_setup_fill_convex_poly4(int W, int H, const int64_t (*v)[2], int role, TcPrim *out) {
     const int npts = 4;
     const int64_t delta = TC_XY_ONE >> 1;
@@ -755,10 +756,22 @@ TC_HD void tc_setup_fill_convex_poly4(int W, int H, const int64_t (*v)[2], int r
     xmax = vx1 > xmax ? vx1 : xmax; xmax = vx2 > xmax ? vx2 : xmax; xmax = vx3 > xmax ? vx3 : xmax;
     xmin = vx1 < xmin ? vx1 : xmin; xmin = vx2 < xmin ? vx2 : xmin; xmin = vx3 < xmin ? vx3 : xmin;
     // outline: edge i runs from vertex i-1 to vertex i (the closing edge first)
+    if (COMPACT) {
+        // one instance of the edge set-up for the four edge roles (block-per-env kernel: the roles run concurrently on
+        // different warps and its code should stay small); role is never TC_ROLE_ALL here
+        if (role >= TC_ROLE_EDGE0 && role < TC_ROLE_EDGE0 + 4) {
+            const int i = role - TC_ROLE_EDGE0;
+            tc_setup_line2(W, H, tc_sel4(i, vx3, vx0, vx1, vx2), tc_sel4(i, vy3, vy0, vy1, vy2), tc_sel4(i, vx0, vx1, vx2, vx3),
+                           tc_sel4(i, vy0, vy1, vy2, vy3), out + TC_SLOT_EDGE0 + i);
+            return;
+        }
+        if (role != TC_ROLE_SPANS) return;
+    } else {
     if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + 0) tc_setup_line2(W, H, vx3, vy3, vx0, vy0, out + TC_SLOT_EDGE0 + 0);
     if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + 1) tc_setup_line2(W, H, vx0, vy0, vx1, vy1, out + TC_SLOT_EDGE0 + 1);
     if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + 2) tc_setup_line2(W, H, vx1, vy1, vx2, vy2, out + TC_SLOT_EDGE0 + 2);
     if (role == TC_ROLE_ALL || role == TC_ROLE_EDGE0 + 3) tc_setup_line2(W, H, vx2, vy2, vx3, vy3, out + TC_SLOT_EDGE0 + 3);
+    }
     if (role != TC_ROLE_ALL && role != TC_ROLE_SPANS) return;
     int k = TC_SLOT_SPAN0;
     xmin = (xmin + delta) >> TC_XY_SHIFT; xmax = (xmax + delta) >> TC_XY_SHIFT;
@@ -818,6 +831,7 @@ TC_HD int64_t tc_cv_round(double v) { return (int64_t)rint(v); } // round half t
 // set every slot to TC_PRIM_NONE). `role` selects which slots this call fills, so that the independent parts of one
 // segment can be set up by different threads (each repeats the cheap pre-clip and quad construction): TC_ROLE_SPANS,
 // TC_ROLE_EDGE0+i, TC_ROLE_CAPS, or TC_ROLE_ALL.
+template <bool COMPACT = false>
 TC_HD void tc_polyline_setup(int W, int H, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int t, int role, TcPrim *out) {
     int64_t ax = x0, ay = y0, bx = x1, by = y1;
     if (t <= 1) {
@@ -838,7 +852,7 @@ TC_HD void tc_polyline_setup(int W, int H, int32_t x0, int32_t y0, int32_t x1, i
             r = ((double)T + odd * TC_XY_ONE * 0.5) / sqrt(r);
             int64_t dpx = tc_cv_round(dy * r), dpy = tc_cv_round(dx * r);
             int64_t v[4][2] = {{P0x + dpx, P0y + dpy}, {P0x - dpx, P0y - dpy}, {P1x - dpx, P1y - dpy}, {P1x + dpx, P1y + dpy}};
-            tc_setup_fill_convex_poly4(W, H, v, role, out);
+            tc_setup_fill_convex_poly4<COMPACT>(W, H, v, role, out);
         }
     }
     if (role == TC_ROLE_ALL || role == TC_ROLE_CAPS) {

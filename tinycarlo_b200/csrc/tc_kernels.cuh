@@ -853,16 +853,19 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRe
             fA[v] = Z < 0;
         }
         __syncthreads();
-        for (int v = tid; v < n; v += NT) fB[v] = fA[v] | (uint8_t)tc_clip_pass_node(ct, sc, fA, v, true, -0.0000001);
-        __syncthreads();
-        for (int v = tid; v < n; v += NT) fA[v] = fB[v] | (uint8_t)tc_clip_pass_node(ct, sc, fB, v, false, -0.0000001);
-        __syncthreads();
-        for (int v = tid; v < n; v += NT) rA[v] = sc.Pz[v] > -max_range;
-        __syncthreads();
-        for (int v = tid; v < n; v += NT) rB[v] = rA[v] | (uint8_t)tc_clip_pass_node(ct, sc, rA, v, true, -max_range);
-        __syncthreads();
-        for (int v = tid; v < n; v += NT) rA[v] = rB[v] | (uint8_t)tc_clip_pass_node(ct, sc, rB, v, false, -max_range);
-        __syncthreads();
+        // camera.py:70-77 near-plane fix-ups, :80-86 range fix-ups (depths is a live view: evaluated on the moved z): the four
+        // ordered passes in ONE loop (one instance of the pass in the code; the flags ping-pong between two arrays)
+        for (int pass = 0; pass < 4; pass++) {
+            const bool range = pass >= 2, outgoing = (pass & 1) == 0;
+            const double tz = range ? -max_range : -0.0000001;
+            uint8_t *src = range ? (outgoing ? rA : rB) : (outgoing ? fA : fB), *dst = range ? (outgoing ? rB : rA) : (outgoing ? fB : fA);
+            if (pass == 2) {
+                for (int v = tid; v < n; v += NT) rA[v] = sc.Pz[v] > -max_range;
+                __syncthreads();
+            }
+            for (int v = tid; v < n; v += NT) dst[v] = src[v] | (uint8_t)tc_clip_pass_node(ct, sc, src, v, outgoing, tz);
+            __syncthreads();
+        }
         for (int v = tid; v < n; v += NT) {
             double u, w;
             tc_project(cam, sc.Px[v], sc.Py[v], sc.Pz[v], u, w);
@@ -903,7 +906,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRe
             if (lane < nseg) {
                 int4 s4 = segs[base + lane];
                 for (int role = warp; role < TC_N_ROLES; role += NT / 32)
-                    tc_polyline_setup(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, role, (TcPrim *)(pw + lane * TC_ENV_SEG_WORDS));
+                    tc_polyline_setup<true>(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, role, (TcPrim *)(pw + lane * TC_ENV_SEG_WORDS));
             }
             __syncthreads();
             TC_TL(long long x = clock64(); tl_setup += x - tc0; tc0 = x);
@@ -913,17 +916,25 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRe
                 const TcPrim *q = (const TcPrim *)(pw + lane * TC_ENV_SEG_WORDS + slot * 8);
                 int items = 0;
                 if (lane < nseg && q->kind != TC_PRIM_NONE) items = tc_prim_items(*q);
-                if (items > 0 && items <= TC_SMALL_PRIM_ITEMS) {
-                    TcPlane pl = {plane, a.H, a.W, 0, a.H, -(int)seg_cls[base + lane] * a.H};
-                    tc_prim_draw(g1, pl, *q);
-                }
+                // round 0: every lane draws its own primitive if it is short; further rounds: the whole warp draws the long
+                // ones, one after the other (one instance of the drawing code serves both)
                 unsigned big = __ballot_sync(0xffffffffu, items > TC_SMALL_PRIM_ITEMS);
-                while (big) {   // the few long ones: the whole warp draws them
-                    const int src = __ffs(big) - 1;
-                    big &= big - 1;
-                    const TcPrim *qq = (const TcPrim *)(pw + src * TC_ENV_SEG_WORDS + slot * 8);
-                    TcPlane pl = {plane, a.H, a.W, 0, a.H, -(int)seg_cls[base + src] * a.H};
-                    tc_prim_draw(g, pl, *qq);
+                bool own = true;
+                while (own || big) {
+                    int src = lane;
+                    bool active = items > 0 && items <= TC_SMALL_PRIM_ITEMS;
+                    TcLanes gg = g1;
+                    if (!own) {
+                        src = __ffs(big) - 1;
+                        big &= big - 1;
+                        active = true;
+                        gg = g;
+                    }
+                    own = false;
+                    if (active) {
+                        TcPlane pl = {plane, a.H, a.W, 0, a.H, -(int)seg_cls[base + src] * a.H};
+                        tc_prim_draw(gg, pl, *(const TcPrim *)(pw + src * TC_ENV_SEG_WORDS + slot * 8));
+                    }
                 }
             }
             __syncthreads();

@@ -39,3 +39,10 @@ print({k: (round(100 * v[0] / tot[0], 1), round(100 * v[1] / tot[1], 1)) for k, 
 print("%-22s %8s %8s %6s" % ("file:line", "inst%", "samples%", "lanes"))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[4]) if len(sys.argv) > 4 else 45]:
     print("%-22s %8.2f %8.2f %6.1f" % ("%s:%d" % k, 100 * v[0] / tot[0], 100 * v[1] / tot[1], v[2] / max(v[0], 1)))
+# coarse phases by source range (tc_core.cuh)
+phases = [("tc_core geometry 450-560", 450, 560), ("clip_line 602-642", 602, 642), ("setup bres/line2 658-698", 658, 698), ("fill_convex setup 700-780", 700, 780),
+          ("polyline_setup 782-822", 782, 822), ("draw prims 825-910", 825, 910), ("plane helpers 576-600", 576, 600)]
+print("--- tc_core.cuh by phase (inst%, samples%)")
+for nm, lo, hi in phases:
+    a = [v for k, v in agg.items() if k[0] == "tc_core.cuh" and lo <= k[1] <= hi]
+    print("%-28s %6.2f %6.2f" % (nm, 100 * sum(v[0] for v in a) / tot[0], 100 * sum(v[1] for v in a) / tot[1]))
