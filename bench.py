@@ -6,7 +6,7 @@ Workload (config.workload): BASELINE.json configs[2] — Knuffingen map, 480x640
 of finished envs; 16384 envs per GPU (weak scaling: per-GPU work is fixed, envs shard by index, no per-step collective;
 NCCL only all-gathers episode statistics).
 
-  python bench.py --gpus 1 --steps 20 --warmup 3                       # this repo's CUDA path
+  python bench.py --gpus 1 --steps 100 --warmup 5                      # this repo's CUDA path
   python bench.py --impl reference --steps 3 --warmup 1                # the CPU arm: oracle port on all host cores
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
@@ -89,9 +89,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_arm(n_envs, steps, warmup, threads):
+def cpu_arm(n_envs, steps, warmup, threads, min_seconds=0.0):
     """The reference's algorithm restated in C (oracle/tc_oracle.c), all host threads via OpenMP, same workload:
-    Knuffingen 480x640 classes, Stanley actions from the info of the previous step. Returns env-steps/s."""
+    Knuffingen 480x640 classes, Stanley actions from the info of the previous step. Runs `steps` lockstep passes, and keeps
+    going until min_seconds have passed. Returns (env-steps/s, seconds, passes)."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
     from oracle import oracle as orc
     from pair_util import oracle_env, stanley_actions
@@ -110,20 +111,23 @@ def cpu_arm(n_envs, steps, warmup, threads):
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    done_steps = 0
+    while done_steps < steps or time.perf_counter() - t0 < min_seconds:
         one()
+        done_steps += 1
     dt = time.perf_counter() - t0
-    return n_envs * steps / dt, dt
+    return n_envs * done_steps / dt, dt, done_steps
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=16384)
-    ap.add_argument("--cpu-envs", type=int, default=0, help="envs of the CPU sample (default: 128 x host threads, at most 4096)")
+    ap.add_argument("--cpu-envs", type=int, default=0, help="envs of the CPU sample (default: 128 x host threads, at most 2048: 3 GB of frames)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="length of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -138,14 +142,15 @@ def main():
         # (the pinned oracle) runs on all host threads instead. Rank 0 only.
         if rank != 0:
             return
-        n = args.cpu_envs or min(128 * threads, 4096)
+        # one "step" of this arm = one lockstep pass over a bounded sample of the workload (n envs instead of 16384 per GPU)
+        n = args.cpu_envs or min(128 * threads, 2048)
         W = max(args.warmup, 1)
-        val, dt = cpu_arm(n, args.steps, W, threads)
+        val, dt, _ = cpu_arm(n, args.steps, W, threads)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": W,
                 "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": {"workload": workload, "cpu_sample": f"{n} envs x {args.steps} steps"},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                 "sample": f"{n} envs x {args.steps} lockstep steps, oracle/tc_oracle.c with OpenMP"},
+                                 "sample": f"{n} envs x {args.steps} lockstep steps ({dt:.1f} s), oracle/tc_oracle.c with OpenMP"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line), flush=True)
         return
@@ -317,10 +322,10 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        n_cpu = args.cpu_envs or min(128 * threads, 4096)
-        val, dt = cpu_arm(n_cpu, 8, 1, threads)
+        n_cpu = args.cpu_envs or min(128 * threads, 2048)
+        val, dt, passes = cpu_arm(n_cpu, 8, 1, threads, min_seconds=args.cpu_seconds)
         cpu_baseline = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{n_cpu} envs x 8 lockstep steps of the same workload, oracle/tc_oracle.c with OpenMP ({dt:.1f} s)"}
+                        "sample": f"{n_cpu} envs x {passes} lockstep steps of the same workload, oracle/tc_oracle.c with OpenMP ({dt:.1f} s)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

@@ -95,6 +95,10 @@ def test_drop_in_surface():
     assert abs(info["velocity"] - min(cfg["car"]["max_velocity"], cfg["car"]["max_acceleration"] / 30)) < 1e-12
     rgb = env.render()
     assert rgb.shape == (32, 48, 3) and rgb.dtype == np.uint8
+    ov = env.render_overview()       # the reference's "human" view: the map with the car on it (renderer.py:19-34)
+    h, w = env.map.dimension
+    assert ov.shape == (int(h * 150), int(w * 150), 3) and (ov == np.array([255, 0, 0], np.uint8)).all(-1).any()
+    assert np.array_equal(env._vec.render_overview(0), ov)
     env.no_observation = True        # render_mode is set, so observations are still produced (env.py:77-81)
     assert env.step({"car_control": [0.5, 0.0], "maneuver": 0})[0].any() or True
     env.close()

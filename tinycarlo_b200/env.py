@@ -8,7 +8,8 @@ Same constructor arguments, action dict, observation array, `info` dict layout, 
 `truncated` semantics as the reference, and the attributes its wrappers and examples touch (`unwrapped.wrapped`,
 `.car.track_width`, `.observation_space_format`, `.no_observation`, `.camera.orientation/.fov/.update_params()`,
 `.config`, `.render_mode`, `.map.get_laneline_names()`). Observations and info values come back as numpy / Python
-objects; the numbers are the float64 state of the kernels. `render_mode="human"` (OpenCV windows) is out of scope."""
+objects; the numbers are the float64 state of the kernels. `render_mode="human"` shows the camera frame and the bird's-eye
+overview (tinycarlo_b200/overview.py) in OpenCV windows like the reference; `render_overview()` returns that image."""
 from typing import Any, Dict, Optional, Tuple, Union
 
 import numpy as np
@@ -117,6 +118,8 @@ class TinyCarloEnv(gc.Env):
         self.car = _CarFacade(self)
         self.camera = _CameraFacade(self)
         self._wrapped = False
+        self._overview = None
+        self._windows = None
         assert render_mode is None or render_mode in self.metadata["render_modes"]
         self.render_mode = render_mode
         self.no_observation = False
@@ -181,12 +184,35 @@ class TinyCarloEnv(gc.Env):
         rew = float(i64) if not self._wrapped else 0
         return self._obs(), rew, bool(terminated[0].item()), bool(truncated[0].item()), self._info()
 
+    def render_overview(self) -> np.ndarray:
+        """The map with the car and its tracked path on it (renderer.py:19-34), RGB uint8."""
+        if self._overview is None:
+            from .overview import OverviewRenderer
+            sim = self.config["sim"]
+            self._overview = OverviewRenderer(self.map, sim.get("overview_pixel_per_meter", 150), node_names=sim.get("render_node_names", False))
+        sf, si = self.car._state()
+        path = [(int(si[2 + 2 * i]), int(si[3 + 2 * i])) for i in range(max(int(si[0]), 0))]
+        return self._overview.render([float(sf[0]), float(sf[1])], float(sf[2]), float(sf[3]), self.car.wheelbase, self.car.track_width, path)
+
     def render(self) -> Optional[np.ndarray]:
+        """env.py:149-174: rgb_array -> the RGB camera frame (whatever the observation format); human -> two OpenCV windows"""
         if self.render_mode == "rgb_array":
             return self.camera.get_last_frame_rgb()
         if self.render_mode == "human":
-            raise NotImplementedError("render_mode='human' (OpenCV windows) is outside the scope of tinycarlo_b200")
+            import cv2
+            if self._windows is None:
+                self._windows = ("Map", "Camera")
+                for w in self._windows:
+                    cv2.namedWindow(w, cv2.WINDOW_NORMAL | cv2.WINDOW_KEEPRATIO | cv2.WINDOW_GUI_NORMAL)
+            cv2.imshow(self._windows[0], self.render_overview())
+            cv2.imshow(self._windows[1], self.camera.get_last_frame_rgb())
+            cv2.waitKey(max(int(self.T * 1000), 1) if self.config["sim"].get("render_realtime", False) else 1)
         return None
 
     def close(self):
+        if self._windows is not None:
+            import cv2
+            for w in self._windows:
+                cv2.destroyWindow(w)
+            self._windows = None
         self._vec.close()

@@ -17,6 +17,7 @@ class MapTables:
                 data: Dict[str, Any] = json.load(f)
         else:
             data = map_json
+        self._validate(data, pixel_per_meter, spawn_points)
         ppm = pixel_per_meter
         self.pixel_per_meter = ppm
         self.dimension = (data.get("height", 0) / ppm, data.get("width", 0) / ppm)  # (height, width) in metres
@@ -47,6 +48,50 @@ class MapTables:
         # nodes that have an outgoing lanepath edge (map.py:62-64 redraws otherwise)
         self.has_successor = np.zeros(len(self.lp_nodes), bool)
         self.has_successor[self.lp_edges[:, 0]] = True
+
+    @staticmethod
+    def _validate(data, ppm, spawn_points):
+        """The reference loads whatever json.load returns and fails later, somewhere in a step (IndexError in a Layer query,
+        endless recursion in sample_spawn, map.py:61-64). Here a bad map file is rejected up front, with the reason."""
+        def bad(msg):
+            raise ValueError("map file: " + msg)
+        if not (isinstance(ppm, (int, float)) and math.isfinite(ppm) and ppm > 0):
+            bad(f"pixel_per_meter must be a positive number, got {ppm!r}")
+        if not isinstance(data, dict):
+            bad("top level must be an object")
+        if not isinstance(data.get("lanelines"), dict) or not data["lanelines"]:
+            bad("'lanelines' must be a non-empty object of laneline layers")
+        if not isinstance(data.get("lanepath"), dict):
+            bad("'lanepath' layer is missing")
+
+        def layer(name, L, need_color):
+            if not isinstance(L, dict) or "nodes" not in L or "edges" not in L:
+                bad(f"layer '{name}' needs 'nodes' and 'edges'")
+            col = L.get("layer_color")
+            if need_color and not (isinstance(col, (list, tuple)) and len(col) == 3 and all(isinstance(v, (int, float)) and 0 <= v <= 255 for v in col)):
+                bad(f"layer '{name}': layer_color must be three values in 0..255")
+            n = len(L["nodes"])
+            for i, p in enumerate(L["nodes"]):
+                if not (isinstance(p, (list, tuple)) and len(p) == 2 and all(isinstance(v, (int, float)) and math.isfinite(v) for v in p)):
+                    bad(f"layer '{name}': node {i} must be two finite numbers")
+            for i, e in enumerate(L["edges"]):
+                if not (isinstance(e, (list, tuple)) and len(e) == 2 and all(isinstance(v, int) and 0 <= v < n for v in e)):
+                    bad(f"layer '{name}': edge {i} = {e!r} does not join two of its {n} nodes")
+            return n
+        for name, L in data["lanelines"].items():
+            layer(name, L, True)
+        n_lp = layer("lanepath", data["lanepath"], False)
+        if n_lp == 0 or not data["lanepath"]["edges"]:
+            bad("the lanepath has no edges: there is nothing to drive on")
+        if spawn_points is not None:
+            has_next = {int(e[0]) for e in data["lanepath"]["edges"]}
+            if len(spawn_points) == 0:
+                bad("spawn_points is empty (omit it to spawn anywhere)")
+            for s_ in spawn_points:
+                if not (isinstance(s_, (int, np.integer)) and 0 <= int(s_) < n_lp):
+                    bad(f"spawn point {s_!r} is not a lanepath node (0..{n_lp - 1})")
+            if not any(int(s_) in has_next for s_ in spawn_points):
+                bad("no spawn point has an outgoing lanepath edge: the spawn draw (map.py:61-64) would never end")
 
     # ---- the reference's Map getters (map.py:39-49), used by the single-env facade
     def get_laneline_names(self) -> List[str]:

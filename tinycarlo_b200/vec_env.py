@@ -303,6 +303,19 @@ class TinyCarloVecEnv:
             _lib.check(self._L.tc_render(self._h, None, _ptr(out), _lib.TC_OBS_RGB, None, None, self._stream()), "tc_render")
         return out
 
+    def render_overview(self, env_index: int = 0, overview_pixel_per_meter: Optional[int] = None) -> np.ndarray:
+        """Bird's-eye view of the map with env `env_index`'s car and tracked path (renderer.py:19-34): a host-side debugging
+        view (reads that env's state back), RGB uint8."""
+        from .overview import OverviewRenderer
+        ppm = int(overview_pixel_per_meter or self.config["sim"].get("overview_pixel_per_meter", 150))
+        if getattr(self, "_overview", None) is None or self._overview.ppm != ppm:
+            self._overview = OverviewRenderer(self.map, ppm, node_names=self.config["sim"].get("render_node_names", False))
+        st = self.state_dict()
+        sf, si = st["sf"][env_index].cpu().numpy(), st["si"][env_index].cpu().numpy()
+        path = [(int(si[2 + 2 * i]), int(si[3 + 2 * i])) for i in range(max(int(si[0]), 0))]
+        return self._overview.render([float(sf[0]), float(sf[1])], float(sf[2]), float(sf[3]), float(self._car_rows[env_index, 0]),
+                                     float(self._car_rows[env_index, 1]), path)
+
     def render_obs(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Re-render self.obs at the current poses (after load_state_dict / set_camera_params)."""
         with torch.cuda.device(self.device):
