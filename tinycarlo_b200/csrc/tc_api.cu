@@ -268,7 +268,11 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     h->proj_smem = tc_proj_smem_bytes(h->max_nodes);
     const size_t plane_budget = 48 * 1024;
     tc_band_geometry(h->H, h->W, 1, plane_budget, &h->rows_per_band_cls, &h->n_bands_cls, &h->plane_words_cls);
-    tc_band_geometry(h->H, h->W, C, plane_budget, &h->rows_per_band_rgb, &h->n_bands_rgb, &h->plane_words_rgb);
+    {
+        size_t rgb_budget = 64 * 1024;   // measured on 480x640: 24/32/40/48/64/96 KB -> 3.02/2.64/2.64/2.49/2.32/4.84 ms per 8192 envs
+        if (const char *kb = getenv("TC_RGB_PLANE_KB")) rgb_budget = (size_t)std::max(4, atoi(kb)) * 1024;
+        tc_band_geometry(h->H, h->W, C, rgb_budget, &h->rows_per_band_rgb, &h->n_bands_rgb, &h->plane_words_rgb);
+    }
     for (int c = 0; c < C; c++) h->max_edges = std::max(h->max_edges, map->ll_edge_off[c + 1] - map->ll_edge_off[c]);
     {
         cudaDeviceProp prop;

@@ -333,26 +333,20 @@ __device__ __forceinline__ void tc_store_plane(uint8_t *out, size_t nbytes, cons
         out[i] = (any && ((plane[i >> 5] >> (i & 31)) & 1)) ? 255 : 0;
 }
 
+// colour of class i as r | g<<8 | b<<16 from the kernel-parameter byte array, with compile-time indexing only: a runtime
+// index makes the compiler copy the whole array into every thread's local memory at kernel entry
+__device__ __forceinline__ uint32_t tc_color24_of(const uint8_t (&colors)[TC_MAX_CLASSES * 3], int i) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < TC_MAX_CLASSES; k++)
+        if (k == i) v = colors[3 * k] | (colors[3 * k + 1] << 8) | (colors[3 * k + 2] << 16);
+    return v;
+}
+
 // RGB composition from C class planes (class c starts at bit c*stride_bits of `planes`; a pad word follows the last
 // plane): byte q of the [rows,W,3] image belongs to pixel q/3, channel q%3, and takes the colour of the LAST class drawn
 // there (painter's order, renderer.py:41-43). 16 output bytes touch at most 6 pixels: one funnel-shifted 6-bit window per
-// class gives the winning colour of each of them; the 16 bytes are then cut out of that 18-byte pixel stream.
-template <int R>
-__device__ __forceinline__ uint4 tc_rgb_cut16(const uint32_t (&col)[6]) {
-    uint32_t w[4];
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int i = R + 4 * m + k; // byte i of the stream: pixel i/3, channel i%3
-            v |= ((col[i / 3] >> (8 * (i % 3))) & 0xffu) << (8 * k);
-        }
-        w[m] = v;
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
+// class gives the winning colour of each of them; the 16 bytes are then cut out of that 18-byte pixel stream by funnel shifts.
 template <int NT>
 __device__ __forceinline__ void tc_store_rgb(uint8_t *out, uint32_t npx, const uint32_t *planes, uint32_t stride_bits, int C,
                                              const uint32_t *color24 /* shared: r | g<<8 | b<<16 per class */, bool any,
@@ -374,31 +368,55 @@ __device__ __forceinline__ void tc_store_rgb(uint8_t *out, uint32_t npx, const u
     for (uint32_t i = tid; i < head; i += NT) out[i] = byte_at(i);
     const uint32_t nvec = (nbytes - head) >> 4;
     uint4 *o4 = (uint4 *)(out + head);
-    for (uint32_t j = tid; j < nvec; j += NT) {
+    auto compose = [&](uint32_t j) -> uint4 {   // the 16 bytes of vector j
         uint32_t q0 = head + 16u * j;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (any) {
-            const uint32_t p0 = q0 / 3u;
-            uint32_t col[6] = {0, 0, 0, 0, 0, 0};
-            uint32_t bits = 0;
-            const bool look = !any_plane || (__funnelshift_r(any_plane[p0 >> 5], any_plane[(p0 >> 5) + 1], p0 & 31) & 0x3fu);
-            if (look) for (int c = 0; c < C; c++) {
-                uint32_t bi = (uint32_t)c * stride_bits + p0;
-                uint32_t w = __funnelshift_r(planes[bi >> 5], planes[(bi >> 5) + 1], bi & 31) & 0x3fu;
-                if (w) {
-                    const uint32_t cc = color24[c];
-#pragma unroll
-                    for (int k = 0; k < 6; k++) col[k] = ((w >> k) & 1u) ? cc : col[k];
-                    bits |= w;
-                }
-            }
-            if (bits) {
-                const uint32_t r = q0 - 3u * p0;
-                v = r == 0 ? tc_rgb_cut16<0>(col) : (r == 1 ? tc_rgb_cut16<1>(col) : tc_rgb_cut16<2>(col));
+        const uint32_t p0 = q0 / 3u;
+        // the 18-byte stream of the 6 pixels the vector touches, in five words (pixel k = bits 24k .. 24k+23); kept in scalars:
+        // an indexed array would live in local memory, and its traffic queues behind the observation stores
+        uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+        uint32_t bits = 0;
+        const bool look = !any_plane || (__funnelshift_r(any_plane[p0 >> 5], any_plane[(p0 >> 5) + 1], p0 & 31) & 0x3fu);
+        if (look) for (int c = 0; c < C; c++) {
+            uint32_t bi = (uint32_t)c * stride_bits + p0;
+            uint32_t w = __funnelshift_r(planes[bi >> 5], planes[(bi >> 5) + 1], bi & 31) & 0x3fu;
+            if (w) {   // painter's order: a later class replaces the pixel
+                const uint32_t cc = color24[c];
+                if (w & 1u) s0 = (s0 & 0xff000000u) | cc;
+                if (w & 2u) { s0 = (s0 & 0x00ffffffu) | (cc << 24); s1 = (s1 & 0xffff0000u) | (cc >> 8); }
+                if (w & 4u) { s1 = (s1 & 0x0000ffffu) | (cc << 16); s2 = (s2 & 0xffffff00u) | (cc >> 16); }
+                if (w & 8u) s2 = (s2 & 0x000000ffu) | (cc << 8);
+                if (w & 16u) s3 = (s3 & 0xff000000u) | cc;
+                if (w & 32u) { s3 = (s3 & 0x00ffffffu) | (cc << 24); s4 = (s4 & 0xffff0000u) | (cc >> 8); }
+                bits |= w;
             }
         }
-        tc_st_cs(o4 + j, v);
+        if (bits) {
+            const uint32_t sh = 8u * (q0 - 3u * p0);   // the vector starts at byte 0, 1 or 2 of the stream
+            v = make_uint4(__funnelshift_r(s0, s1, sh), __funnelshift_r(s1, s2, sh), __funnelshift_r(s2, s3, sh), __funnelshift_r(s3, s4, sh));
+        }
+        return v;
+    };
+    // A frame is mostly background. 32 words of the OR plane = 1024 pixels = 3072 bytes = 192 vectors: a warp looks at 32
+    // words at once and, when they are all empty, writes its 6 x 32 zero vectors without any per-vector work.
+    uint32_t done = 0;
+    if (any && any_plane && head == 0) {
+        const uint32_t ngroups = nvec / 192u;
+        const uint32_t lane = tid & 31, warp = tid >> 5;
+        for (uint32_t gi = warp; gi < ngroups; gi += NT / 32) {
+            const unsigned nz = __ballot_sync(0xffffffffu, any_plane[gi * 32u + lane] != 0u);
+            const uint32_t j0 = gi * 192u + lane;
+            if (nz == 0) {
+                const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int k = 0; k < 6; k++) tc_st_cs(o4 + j0 + 32u * k, z);
+            } else {
+                for (int k = 0; k < 6; k++) tc_st_cs(o4 + j0 + 32u * k, compose(j0 + 32u * k));
+            }
+        }
+        done = ngroups * 192u;
     }
+    for (uint32_t j = done + tid; j < nvec; j += NT) tc_st_cs(o4 + j, any ? compose(j) : make_uint4(0, 0, 0, 0));
     for (uint32_t i = head + (nvec << 4) + tid; i < nbytes; i += NT) out[i] = byte_at(i);
 }
 
@@ -459,8 +477,11 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_classes_kernel(co
 
 // rgb, large frames: grid = N*n_bands blocks; C class planes of the band; later classes overwrite earlier ones
 // (renderer.py:41-43). Segments come from tc_project_kernel; set-up is split by role over the warps like in the fused kernel.
+// shared memory: [C class planes + pad word][OR of the class planes + pad word][primitive slots]
+__host__ __device__ inline size_t tc_raster_rgb_planes_bytes(int C, int plane_words) { return (((size_t)C * plane_words + 1) * 4 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t tc_raster_rgb_any_bytes(int plane_words) { return (((size_t)plane_words + 1) * 4 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t tc_raster_rgb_smem_bytes(int C, int plane_words) {
-    return ((((size_t)C * plane_words + 1) * 4 + 15) & ~(size_t)15) + (size_t)TC_SETUP_CHUNK * TC_MAX_PRIMS_PER_SEG * sizeof(TcPrim);
+    return tc_raster_rgb_planes_bytes(C, plane_words) + tc_raster_rgb_any_bytes(plane_words) + (size_t)TC_SETUP_CHUNK * TC_MAX_PRIMS_PER_SEG * sizeof(TcPrim);
 }
 __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const TcRasterArgs a) {
     extern __shared__ __align__(16) uint32_t planes[];
@@ -473,7 +494,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const 
     if (a.mask && !a.mask[env]) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < TC_MAX_CLASSES) {
-        color24[tid] = a.colors[3 * tid] | (a.colors[3 * tid + 1] << 8) | (a.colors[3 * tid + 2] << 16);
+        color24[tid] = tc_color24_of(a.colors, tid);
         cls_cnt[tid] = tid < C ? a.seg_count[(size_t)env * C + tid] : 0;
     }
     __syncthreads();
@@ -487,7 +508,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const 
         for (int i = tid; i < C * a.plane_words + 1; i += TC_RASTER_THREADS) planes[i] = 0;
         const int t = a.thickness[env];
         TcLanes g = {lane, 32};
-        TcPrim *prims = (TcPrim *)((unsigned char *)planes + ((((size_t)C * a.plane_words + 1) * 4 + 15) & ~(size_t)15));
+        TcPrim *prims = (TcPrim *)((unsigned char *)planes + tc_raster_rgb_planes_bytes(C, a.plane_words) + tc_raster_rgb_any_bytes(a.plane_words));
         for (int win = 0; win < total; win += TC_RASTER_THREADS) {
             // segments of this window that can touch the band's rows (all primitives stay within t+2 rows of the end points)
             if (tid == 0) list_n = 0;
@@ -525,7 +546,18 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const 
             }
         }
     }
-    tc_store_rgb<TC_RASTER_THREADS>(out, (uint32_t)((y_hi - y_lo) * a.W), planes, (uint32_t)a.plane_words * 32u, C, color24, drew);
+    // a frame is mostly background: the OR of the class planes tells the composition which 6-pixel windows have anything in them
+    uint32_t *any_plane = (uint32_t *)((unsigned char *)planes + tc_raster_rgb_planes_bytes(C, a.plane_words));
+    if (drew) {
+        for (int i = tid; i <= a.plane_words; i += TC_RASTER_THREADS) {
+            uint32_t v = 0;
+            if (i < a.plane_words)
+                for (int c = 0; c < C; c++) v |= planes[(size_t)c * a.plane_words + i];
+            any_plane[i] = v;
+        }
+        __syncthreads();
+    }
+    tc_store_rgb<TC_RASTER_THREADS>(out, (uint32_t)((y_hi - y_lo) * a.W), planes, (uint32_t)a.plane_words * 32u, C, color24, drew, any_plane);
 }
 
 // ------------------------------------------------------------------------------------------------ fused camera pass + rasterise + store
@@ -626,7 +658,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const 
         // camera pass would push the kernel over 64 registers, and spills are local-memory traffic behind the stores
         if (RGB && tid >= 64 && tid < 64 + TC_MAX_CLASSES) {
             const int cc = tid - 64;
-            s_color24[cc] = a.colors[3 * cc] | (a.colors[3 * cc + 1] << 8) | (a.colors[3 * cc + 2] << 16);
+            s_color24[cc] = tc_color24_of(a.colors, cc);
         }
         if (tid < 12) s_pose[tid] = a.pose[(size_t)env * 12 + tid];
         else if (tid < 12 + (TC_CAM_MAX_RANGE - TC_CAM_FX + 1)) s_cam[TC_CAM_FX + tid - 12] = a.cam[(size_t)env * TC_CAM_N + TC_CAM_FX + tid - 12];
@@ -825,7 +857,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRe
     }
     if (RGB && tid >= 64 && tid < 64 + TC_MAX_CLASSES) {
         const int cc = tid - 64;
-        s_color24[cc] = a.colors[3 * cc] | (a.colors[3 * cc + 1] << 8) | (a.colors[3 * cc + 2] << 16);
+        s_color24[cc] = tc_color24_of(a.colors, cc);
     }
     if (tid >= 32 && tid < 44) s_pose[tid - 32] = a.pose[(size_t)env * 12 + tid - 32];
     else if (tid >= 44 && tid < 44 + (TC_CAM_MAX_RANGE - TC_CAM_FX + 1)) s_cam[TC_CAM_FX + tid - 44] = a.cam[(size_t)env * TC_CAM_N + TC_CAM_FX + tid - 44];
