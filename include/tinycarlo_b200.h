@@ -113,6 +113,8 @@ TC_API int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_env
 TC_API int tc_destroy(TcHandle *h);
 
 TC_API int tc_set_car_params(TcHandle *h, const double *dev_params /*[N,TC_CP_N]*/, void *stream);
+/* Handles that render small frames with one block per env (C*H*W <= 128 KB) read the rows back in this call and rebuild
+ * their visible-set tables when the cameras' reach changed: the call then synchronises the stream (it is a set-up call). */
 TC_API int tc_set_camera_params(TcHandle *h, const double *dev_cam /*[N,TC_CAM_N]*/, const int32_t *dev_thickness /*[N]*/, void *stream);
 TC_API int tc_set_wrapped(TcHandle *h, int32_t wrapped); /* 1: reward 0 / terminated false (env.py:137-138) */
 
