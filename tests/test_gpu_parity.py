@@ -444,3 +444,82 @@ def test_cuda_policy_formats_equal_the_u8_masks(res, n):
             assert np.array_equal(bits * 255, ref.cpu().numpy())
     for e in envs.values():
         e.close()
+
+
+def test_cuda_visible_set_tables_do_not_change_frames():
+    """Block-per-env kernel: frames rendered through the per-cell visible-set tables equal those of the whole-graph camera pass
+    (TC_CULL=0), for shipped and for per-env randomised cameras, over a driven rollout with auto-reset."""
+    import os
+    n = 4096
+    cfg = make_config("knuffingen", "classes", cam={"resolution": [128, 160]}, car={"max_velocity": 0.3})
+    rng = np.random.default_rng(11)
+    env = _vec(cfg, n, autoreset="next_step")
+    info = env.cull_info()
+    assert info["radius"] > 0 and info["max_nodes"] < 0.6 * len(env.map.ll_nodes), info
+    os.environ["TC_CULL"] = "0"
+    try:
+        ref = _vec(cfg, n, autoreset="next_step")
+        assert ref.cull_info()["radius"] == -1.0
+        for phase in range(2):
+            if phase == 1:   # config-5 style cameras: the tables are rebuilt for the largest reach
+                kw = dict(orientation=np.stack([rng.uniform(10, 30, n), rng.uniform(-3, 3, n), rng.uniform(-20, 20, n)], 1).round(1),
+                          fov=rng.integers(70, 120, n).astype(float), max_range=rng.uniform(0.3, 0.8, n).round(2))
+                ref.set_camera_params(**kw)
+                del os.environ["TC_CULL"]
+                env.set_camera_params(**kw)
+                os.environ["TC_CULL"] = "0"
+                assert env.cull_info()["radius"] > info["radius"] and ref.cull_info()["radius"] == -1.0
+            env.reset(seed=3)
+            ref.reset(seed=3)
+            assert torch.equal(env.obs, ref.obs)
+            for t in range(30):
+                cc = torch.from_numpy(rng.uniform(-1, 1, (n, 2)).astype(np.float32)).cuda()
+                man = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)).cuda()
+                env.step({"car_control": cc, "maneuver": man})
+                ref.step({"car_control": cc, "maneuver": man})
+                assert torch.equal(env.obs, ref.obs), (phase, t)
+            assert env.obs.any()
+        ref.close()
+    finally:
+        os.environ.pop("TC_CULL", None)
+    env.close()
+
+
+def test_cuda_step_is_graph_capturable():
+    """step() enqueues kernels on torch's current stream and neither allocates nor synchronises, so a rollout loop (policy ops +
+    step, in-kernel autoreset included) can be captured in a CUDA graph; replays equal eager stepping bit for bit."""
+    n = 1024
+    cfg = make_config("simple_layout", "classes", cam={"resolution": [84, 84]}, car={"max_velocity": 0.15})
+    envs = [_vec(cfg, n, autoreset="next_step") for _ in range(2)]
+    for e in envs:
+        e.reset(seed=4)
+    cc = [torch.zeros((n, 2), device="cuda") for _ in range(2)]
+    man = torch.zeros(n, dtype=torch.int32, device="cuda")
+
+    def policy_and_step(e, c):   # Stanley controller on the previous step's info (examples/stanley_control.py:56-58)
+        o = e.out
+        c[:, 0] = 0.9
+        c[:, 1] = (o["heading_error"] + torch.atan2(4.0 * o["cte"], torch.full_like(o["cte"], 0.8))) * (180.0 / np.pi / 30.0)
+        e.step({"car_control": c, "maneuver": man})
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):          # warm-up on the side stream, as torch's capture rules ask
+            policy_and_step(envs[0], cc[0])
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(3):
+        policy_and_step(envs[1], cc[1])
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        policy_and_step(envs[0], cc[0])
+    policy_and_step(envs[1], cc[1])   # the captured call did not execute: one eager step for the twin ... and one replay
+    g.replay()
+    for t in range(60):
+        g.replay()
+        policy_and_step(envs[1], cc[1])
+        if t % 10 == 9:
+            torch.cuda.synchronize()
+            assert torch.equal(envs[0].obs, envs[1].obs) and torch.equal(envs[0].out["info_f64"], envs[1].out["info_f64"]), t
+            assert torch.equal(envs[0].done_flags, envs[1].done_flags)
+    for e in envs:
+        e.close()

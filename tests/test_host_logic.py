@@ -155,3 +155,20 @@ def test_vectorised_pcg64_equals_numpy_generator():
     w = VecPCG64()
     w.load_state_dict(st)
     assert np.array_equal(w.bounded(1000), a)
+
+
+def test_headline_kernel_keeps_its_register_budget():
+    """the per-class render kernel (u8) sits at 64 registers without spills; local-memory traffic behind
+    the observation stores costs it the HBM write roofline. Checked on the built library (no GPU needed)."""
+    import re
+    import shutil
+    import subprocess
+    from tinycarlo_b200 import _lib
+    if shutil.which("cuobjdump") is None or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    m = re.search(r"Function _Z24tc_render_classes_kernelILi256ELi0EEv12TcRenderArgs:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert m, "headline kernel not found in the library"
+    assert int(m.group(1)) <= 64 and int(m.group(2)) == 0, m.group(0)
+    m = re.search(r"Function _Z20tc_render_env_kernelILi256ELi0EEv15TcRenderEnvArgs:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert m and int(m.group(1)) <= 64, "block-per-env kernel missing or over its register budget"
