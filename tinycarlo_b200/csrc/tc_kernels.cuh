@@ -17,6 +17,7 @@
 #define TC_PROJ_THREADS 128
 #define TC_RASTER_THREADS 256
 #define TC_SETUP_CHUNK 16 // segments set up per round (one thread per segment and role), then drawn by all warps
+#define TC_ENV_SEG_WORDS (12 * 8 + 1) // block-per-env kernels: a segment's 12 primitive slots of 8 words, padded so that lanes reading one slot of 32 segments hit 32 banks
 
 // ------------------------------------------------------------------------------------------------ TMA / mbarrier PTX
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -368,16 +369,14 @@ __device__ __forceinline__ void tc_store_rgb(uint8_t *out, uint32_t npx, const u
     for (uint32_t i = tid; i < head; i += NT) out[i] = byte_at(i);
     const uint32_t nvec = (nbytes - head) >> 4;
     uint4 *o4 = (uint4 *)(out + head);
-    auto compose = [&](uint32_t j) -> uint4 {   // the 16 bytes of vector j
-        uint32_t q0 = head + 16u * j;
-        uint4 v = make_uint4(0, 0, 0, 0);
+    // the 16 bytes of vector j from the class planes (the caller knows, or does not care, that its window is not empty)
+    auto compose = [&](uint32_t j) -> uint4 {
+        const uint32_t q0 = head + 16u * j;
         const uint32_t p0 = q0 / 3u;
         // the 18-byte stream of the 6 pixels the vector touches, in five words (pixel k = bits 24k .. 24k+23); kept in scalars:
         // an indexed array would live in local memory, and its traffic queues behind the observation stores
         uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-        uint32_t bits = 0;
-        const bool look = !any_plane || (__funnelshift_r(any_plane[p0 >> 5], any_plane[(p0 >> 5) + 1], p0 & 31) & 0x3fu);
-        if (look) for (int c = 0; c < C; c++) {
+        for (int c = 0; c < C; c++) {
             uint32_t bi = (uint32_t)c * stride_bits + p0;
             uint32_t w = __funnelshift_r(planes[bi >> 5], planes[(bi >> 5) + 1], bi & 31) & 0x3fu;
             if (w) {   // painter's order: a later class replaces the pixel
@@ -388,35 +387,66 @@ __device__ __forceinline__ void tc_store_rgb(uint8_t *out, uint32_t npx, const u
                 if (w & 8u) s2 = (s2 & 0x000000ffu) | (cc << 8);
                 if (w & 16u) s3 = (s3 & 0xff000000u) | cc;
                 if (w & 32u) { s3 = (s3 & 0x00ffffffu) | (cc << 24); s4 = (s4 & 0xffff0000u) | (cc >> 8); }
-                bits |= w;
             }
         }
-        if (bits) {
-            const uint32_t sh = 8u * (q0 - 3u * p0);   // the vector starts at byte 0, 1 or 2 of the stream
-            v = make_uint4(__funnelshift_r(s0, s1, sh), __funnelshift_r(s1, s2, sh), __funnelshift_r(s2, s3, sh), __funnelshift_r(s3, s4, sh));
-        }
-        return v;
+        const uint32_t sh = 8u * (q0 - 3u * p0);   // the vector starts at byte 0, 1 or 2 of the stream
+        return make_uint4(__funnelshift_r(s0, s1, sh), __funnelshift_r(s1, s2, sh), __funnelshift_r(s2, s3, sh), __funnelshift_r(s3, s4, sh));
     };
-    // A frame is mostly background. 32 words of the OR plane = 1024 pixels = 3072 bytes = 192 vectors: a warp looks at 32
-    // words at once and, when they are all empty, writes its 6 x 32 zero vectors without any per-vector work.
-    uint32_t done = 0;
-    if (any && any_plane && head == 0) {
-        const uint32_t ngroups = nvec / 192u;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    if (!any) {
+        for (uint32_t j = tid; j < nvec; j += NT) tc_st_cs(o4 + j, zero);
+    } else if (!any_plane) {
+        for (uint32_t j = tid; j < nvec; j += NT) tc_st_cs(o4 + j, compose(j));
+    } else {
+        // A frame is mostly background, and the few vectors that are not are scattered over the lanes of a warp: composing
+        // them where they fall runs the class loop with 2-3 active lanes. So a warp writes the empty vectors at once and
+        // queues the others (warp-private queue in shared memory); whenever 32 are waiting they are composed with all lanes.
+        __shared__ uint32_t wq[NT / 32][64];
         const uint32_t lane = tid & 31, warp = tid >> 5;
-        for (uint32_t gi = warp; gi < ngroups; gi += NT / 32) {
-            const unsigned nz = __ballot_sync(0xffffffffu, any_plane[gi * 32u + lane] != 0u);
-            const uint32_t j0 = gi * 192u + lane;
-            if (nz == 0) {
-                const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int k = 0; k < 6; k++) tc_st_cs(o4 + j0 + 32u * k, z);
-            } else {
-                for (int k = 0; k < 6; k++) tc_st_cs(o4 + j0 + 32u * k, compose(j0 + 32u * k));
+        uint32_t qn = 0;   // warp-uniform
+        auto visit = [&](uint32_t j, bool valid) {   // called by all lanes of the warp
+            bool look = false;
+            if (valid) {
+                const uint32_t p0 = (head + 16u * j) / 3u;
+                look = (__funnelshift_r(any_plane[p0 >> 5], any_plane[(p0 >> 5) + 1], p0 & 31) & 0x3fu) != 0u;
+                if (!look) tc_st_cs(o4 + j, zero);
             }
+            const unsigned m = __ballot_sync(0xffffffffu, look);
+            if (m) {
+                if (look) wq[warp][qn + __popc(m & ((1u << lane) - 1u))] = j;
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32u) {
+                    const uint32_t jj = wq[warp][qn - 32u + lane];
+                    tc_st_cs(o4 + jj, compose(jj));
+                    qn -= 32u;
+                    __syncwarp();
+                }
+            }
+        };
+        uint32_t done = 0;
+        if (head == 0) {
+            // 32 words of the OR plane = 1024 pixels = 3072 bytes = 192 vectors: when they are all empty the warp writes its
+            // 6 x 32 zero vectors without any per-vector work
+            const uint32_t ngroups = nvec / 192u;
+            for (uint32_t gi = warp; gi < ngroups; gi += NT / 32) {
+                const unsigned nz = __ballot_sync(0xffffffffu, any_plane[gi * 32u + lane] != 0u);
+                const uint32_t j0 = gi * 192u + lane;
+                if (nz == 0) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) tc_st_cs(o4 + j0 + 32u * k, zero);
+                } else {
+                    for (int k = 0; k < 6; k++) visit(j0 + 32u * k, true);
+                }
+            }
+            done = ngroups * 192u;
         }
-        done = ngroups * 192u;
+        for (uint32_t base = done + warp * 32u; base < nvec; base += NT) visit(base + lane, base + lane < nvec);
+        if (lane < qn) {
+            const uint32_t jj = wq[warp][lane];
+            tc_st_cs(o4 + jj, compose(jj));
+        }
     }
-    for (uint32_t j = done + tid; j < nvec; j += NT) tc_st_cs(o4 + j, any ? compose(j) : make_uint4(0, 0, 0, 0));
     for (uint32_t i = head + (nvec << 4) + tid; i < nbytes; i += NT) out[i] = byte_at(i);
 }
 
@@ -558,6 +588,123 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const 
         __syncthreads();
     }
     tc_store_rgb<TC_RASTER_THREADS>(out, (uint32_t)((y_hi - y_lo) * a.W), planes, (uint32_t)a.plane_words * 32u, C, color24, drew, any_plane);
+}
+
+// rgb, large frames, block per env: the polyline set-up is the latency-bound part of a band block, and a segment that
+// crosses several bands used to be set up in each of them. Here a block owns a whole frame: it sets up all segments of the
+// env ONCE (rounds of 32, lane = segment, warp = role, primitives kept in shared memory) and then walks the row bands -
+// zero the C band planes, draw the primitives that can touch the band, OR the planes, compose and stream the rows out.
+// Frames with more than TC_RGBE_MAX_SEGS visible segments (the list does not fit) redo the set-up per band in rounds.
+// shared memory: [C band planes + pad][OR plane + pad][primitive slots of TC_RGBE_MAX_SEGS segments][per-segment class, row range]
+#define TC_RGBE_MAX_SEGS 64
+__host__ __device__ inline size_t tc_rgbe_off_prims(int C, int plane_words) { return tc_raster_rgb_planes_bytes(C, plane_words) + tc_raster_rgb_any_bytes(plane_words); }
+__host__ __device__ inline size_t tc_rgbe_smem_bytes(int C, int plane_words) {
+    return tc_rgbe_off_prims(C, plane_words) + (((size_t)TC_RGBE_MAX_SEGS * TC_ENV_SEG_WORDS * 4 + 15) & ~(size_t)15);
+}
+__global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_raster_rgb_env_kernel(const TcRasterArgs a) {
+    extern __shared__ __align__(16) uint32_t planes[];
+    __shared__ uint32_t color24[TC_MAX_CLASSES];
+    __shared__ int cls_cnt[TC_MAX_CLASSES];
+    __shared__ int seg_c[TC_RGBE_MAX_SEGS], seg_lo[TC_RGBE_MAX_SEGS], seg_hi[TC_RGBE_MAX_SEGS];
+    __shared__ uint16_t list[TC_RGBE_MAX_SEGS * TC_MAX_PRIMS_PER_SEG];
+    __shared__ int list_n;
+    __shared__ unsigned band_mask;   // bit b: some segment of the current slots can touch band b (n_bands <= 32, else all ones)
+    const int C = a.n_classes;
+    const int env = blockIdx.x;
+    if (a.mask && !a.mask[env]) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < TC_MAX_CLASSES) {
+        color24[tid] = tc_color24_of(a.colors, tid);
+        cls_cnt[tid] = tid < C ? a.seg_count[(size_t)env * C + tid] : 0;
+    }
+    __syncthreads();
+    int total = 0;
+    for (int c = 0; c < C; c++) total += cls_cnt[c];
+    const int t = a.thickness[env];
+    uint32_t *any_plane = (uint32_t *)((unsigned char *)planes + tc_raster_rgb_planes_bytes(C, a.plane_words));
+    int32_t *pw = (int32_t *)((unsigned char *)planes + tc_rgbe_off_prims(C, a.plane_words));
+    const TcLanes g = {lane, 32};
+    // set-up of the segments [first, first + n) of the env (n <= TC_RGBE_MAX_SEGS) into the primitive slots
+    auto setup = [&](int first, int n) {
+        if (tid == 0) band_mask = 0;
+        for (int i = tid; i < n * TC_MAX_PRIMS_PER_SEG; i += TC_RASTER_THREADS)
+            pw[(i / TC_MAX_PRIMS_PER_SEG) * TC_ENV_SEG_WORDS + (i % TC_MAX_PRIMS_PER_SEG) * 8] = TC_PRIM_NONE;
+        __syncthreads();
+        for (int sub = 0; sub < n; sub += 32) {
+            const int sl = sub + lane;
+            if (sl < n) {
+                int k = first + sl, c = 0;
+                while (k >= cls_cnt[c]) { k -= cls_cnt[c]; c++; }
+                const int4 s4 = *(const int4 *)(a.seg + ((size_t)env * a.sum_edges + a.edge_off[c] + k) * 4);
+                if (warp == 0) {
+                    seg_c[sl] = c;
+                    // every primitive of a segment stays within t + 2 rows of its end points
+                    const long long lo = (long long)min(s4.y, s4.w) - t - 2, hi = (long long)max(s4.y, s4.w) + t + 2;
+                    const int ilo = (int)max(lo, (long long)-1), ihi = (int)min(hi, (long long)a.H);
+                    seg_lo[sl] = ilo; seg_hi[sl] = ihi;
+                    if (ihi >= 0 && ilo < a.H) {
+                        const int b0 = max(ilo, 0) / a.rows_per_band, b1 = min(ihi, a.H - 1) / a.rows_per_band;
+                        unsigned mk = a.n_bands > 32 ? 0xffffffffu : 0u;
+                        for (int b = b0; b <= b1 && a.n_bands <= 32; b++) mk |= 1u << b;
+                        atomicOr(&band_mask, mk);
+                    }
+                }
+                for (int role = warp; role < TC_N_ROLES; role += TC_RASTER_THREADS / 32)
+                    tc_polyline_setup<true>(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, role, (TcPrim *)(pw + sl * TC_ENV_SEG_WORDS));
+            }
+        }
+        __syncthreads();
+    };
+    // the primitives of the current slots that can touch rows [y_lo, y_hi): found by all threads at once (one primitive
+    // each), listed in shared memory, then drawn warp by warp
+    auto draw = [&](int n, int y_lo, int y_hi) {
+        if (tid == 0) list_n = 0;
+        __syncthreads();
+        for (int p = tid; p < n * TC_MAX_PRIMS_PER_SEG; p += TC_RASTER_THREADS) {
+            const int sl = p / TC_MAX_PRIMS_PER_SEG;
+            if (seg_hi[sl] < y_lo || seg_lo[sl] >= y_hi) continue;
+            if (pw[sl * TC_ENV_SEG_WORDS + (p % TC_MAX_PRIMS_PER_SEG) * 8] == TC_PRIM_NONE) continue;
+            list[atomicAdd(&list_n, 1)] = (uint16_t)p;
+        }
+        __syncthreads();
+        const int m = list_n;
+        for (int i = warp; i < m; i += TC_RASTER_THREADS / 32) {
+            const int p = list[i], sl = p / TC_MAX_PRIMS_PER_SEG;
+            const TcPrim &q = *(const TcPrim *)(pw + sl * TC_ENV_SEG_WORDS + (p % TC_MAX_PRIMS_PER_SEG) * 8);
+            TcPlane pl = {planes + (size_t)seg_c[sl] * a.plane_words, a.H, a.W, y_lo, y_hi, y_lo};
+            tc_prim_draw(g, pl, q);
+        }
+    };
+    const bool once = total <= TC_RGBE_MAX_SEGS;
+    if (once && total > 0) setup(0, total);
+    for (int band = 0; band < a.n_bands; band++) {
+        const int y_lo = band * a.rows_per_band;
+        const int y_hi = min(a.H, y_lo + a.rows_per_band);
+        uint8_t *out = a.obs + ((size_t)env * a.H + y_lo) * a.W * 3;
+        const bool drew = once ? (total > 0 && ((band_mask >> (band & 31)) & 1u)) : total > 0;
+        if (drew) {
+            for (int i = tid; i < C * a.plane_words + 1; i += TC_RASTER_THREADS) planes[i] = 0;
+            __syncthreads();
+            if (once) draw(total, y_lo, y_hi);
+            else
+                for (int first = 0; first < total; first += TC_RGBE_MAX_SEGS) {
+                    const int n = min(TC_RGBE_MAX_SEGS, total - first);
+                    setup(first, n);
+                    draw(n, y_lo, y_hi);
+                    __syncthreads();
+                }
+            __syncthreads();
+            for (int i = tid; i <= a.plane_words; i += TC_RASTER_THREADS) {
+                uint32_t v = 0;
+                if (i < a.plane_words)
+                    for (int c = 0; c < C; c++) v |= planes[(size_t)c * a.plane_words + i];
+                any_plane[i] = v;
+            }
+            __syncthreads();
+        }
+        tc_store_rgb<TC_RASTER_THREADS>(out, (uint32_t)((y_hi - y_lo) * a.W), planes, (uint32_t)a.plane_words * 32u, C, color24, drew, any_plane);
+        __syncthreads();   // the next band reuses the planes
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ fused camera pass + rasterise + store
@@ -781,7 +928,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const 
 //    plane and primitive slots overlay the projected coordinates, flags and tables.
 #define TC_SMALL_PRIM_ITEMS 48
 #define TC_ENV_CHUNK 32
-#define TC_ENV_SEG_WORDS (TC_MAX_PRIMS_PER_SEG * 8 + 1) // 12 slots of 8 words, padded: lanes reading one slot of 32 segments hit 32 banks
 __device__ __forceinline__ int tc_prim_items(const TcPrim &q) {
     if (q.kind == TC_PRIM_LINE2) return q.a[4] + 1;
     if (q.kind == TC_PRIM_SPAN) return q.a[2] - q.a[1];
