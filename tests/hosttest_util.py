@@ -44,6 +44,7 @@ def ht():
         L.ht_cull_radius_of.restype = C.c_double
         L.ht_cull_radius_of.argtypes = [vp, i, i]
         L.ht_project_culled.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp]
+        L.ht_nearest.argtypes = [vp, i, vp, i, i, vp, vp, vp]
         L.ht_polyline.argtypes = [vp, i, i, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i, i, i, i]
         _ht = L
     return _ht

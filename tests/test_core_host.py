@@ -240,3 +240,35 @@ def test_cull_radius_rejects_cameras_outside_the_argument():
     assert ht().ht_cull_radius_of(P(ground), 128, 160) < 0
     inf = row.copy(); inf[16] = np.inf
     assert ht().ht_cull_radius_of(P(inf), 128, 160) < 0
+
+
+@pytest.mark.parametrize("map_name", ["knuffingen", "simple_layout", "formula_student_track", "formula_student_skidpad"])
+def test_nearest_laneline_index_equals_the_full_scan(map_name):
+    """tc_build_near: the candidate list of a ground cell contains every edge that can be the arg-min of d(p,n0)+d(p,n1)
+    (layer.py:33-44) for a point of the cell, so the indexed search returns what the scan over all edges returns - on the
+    lines, between them, on cell borders, on nodes (ties -> first edge) and outside the grid (plain scan)."""
+    from pair_util import make_config
+    cfg = make_config(map_name, "classes", spawn=None)
+    tables = MapTables(resolve_map_path(cfg["map"], None), cfg["map"]["pixel_per_meter"], None)
+    env = HostCore(tables, 1, np.zeros(8), np.zeros(20), 1, 8, 8)
+    rng = np.random.default_rng(len(map_name))
+    nodes = np.asarray(tables.ll_nodes, np.float64).reshape(-1, 2)
+    lo, hi = nodes.min(0), nodes.max(0)
+    n = 20000
+    pts = np.concatenate([nodes[rng.integers(0, len(nodes), n // 4)] + rng.normal(0, 0.05, (n // 4, 2)),     # next to the lines
+                          rng.uniform(lo - 1.2, hi + 1.2, (n // 4, 2)),                                    # anywhere, also outside the grid
+                          nodes[rng.integers(0, len(nodes), n // 4)],                                      # on nodes: exact ties between adjacent edges
+                          0.5 * (nodes[rng.integers(0, len(nodes), n // 4)] + nodes[rng.integers(0, len(nodes), n // 4)])])
+    pts = np.ascontiguousarray(pts)
+    C = tables.n_classes
+    full = np.zeros((len(pts), C), np.int32)
+    ht().ht_nearest(env.h, len(pts), P(pts), 0, 1, P(full), None, None)
+    info = np.zeros(3)
+    cand = np.zeros(len(pts), np.int32)
+    for nlanes in (1, 32):
+        got = np.zeros_like(full)
+        ht().ht_nearest(env.h, len(pts), P(pts), 1, nlanes, P(got), P(cand), P(info))
+        assert np.array_equal(got, full), (map_name, nlanes, int((got != full).sum()))
+    assert info[0] > 1000 and (cand >= 0).mean() > 0.7, "the index should cover the map"
+    m_total = int(tables.ll_edge_off[-1])
+    assert info[1] < 0.25 * m_total / C + 8, ("lists should be short", info)

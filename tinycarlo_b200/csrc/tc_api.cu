@@ -77,6 +77,10 @@ struct TcHandle {
     // block-per-env kernel: visible-set tables (tc_cull.h), rebuilt when the camera parameters change
     std::vector<int32_t> m_node_off, m_edge_off, m_edges; // host copy of the laneline tables (the builder's input)
     std::vector<double> m_nodes;
+    // nearest-laneline index of the tracking kernel (tc_cull.h tc_build_near)
+    TcNear near_h;                 // geometry (the tables themselves live on the device)
+    int32_t *d_near_off = nullptr;
+    uint16_t *d_near_edge = nullptr;
     TcCellBlob *d_cell_desc = nullptr;
     unsigned char *d_cell_blob = nullptr;
     TcCullGrid cull_grid{};
@@ -243,6 +247,21 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     for (int c = 0; c <= C; c++) h->edge_off_h[c] = map->ll_edge_off[c];
     TC_TRYH(tc_dev_alloc(h, &h->d_edge_off, (size_t)C + 1));
     TC_CUDAH(cudaMemcpy(h->d_edge_off, map->ll_edge_off, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice));
+
+    {
+        // nearest-laneline index: ~16k ground cells over the laneline bounding box + 1 m (farther out the kernel scans all edges)
+        TcNear nr;
+        const char *ne = getenv("TC_NEAR_INDEX");
+        if (!(ne && atoi(ne) == 0)) tc_build_near(map, 1.0, 16384, nr);
+        if (nr.nx > 0) {
+            TC_TRYH(tc_dev_alloc(h, &h->d_near_off, nr.off.size()));
+            TC_CUDAH(cudaMemcpy(h->d_near_off, nr.off.data(), nr.off.size() * 4, cudaMemcpyHostToDevice));
+            TC_TRYH(tc_dev_alloc(h, &h->d_near_edge, nr.edge.size()));
+            TC_CUDAH(cudaMemcpy(h->d_near_edge, nr.edge.data(), nr.edge.size() * 2, cudaMemcpyHostToDevice));
+            h->near_h = nr;
+            h->near_h.off.clear(); h->near_h.off.shrink_to_fit(); h->near_h.edge.clear(); h->near_h.edge.shrink_to_fit();
+        }
+    }
 
     // ---- per-env buffers
     const size_t N = (size_t)num_envs;
@@ -469,6 +488,8 @@ static int tc_launch_track(TcHandle *h, int mode, const float *cc, const int32_t
     ta.blob = h->d_blob; ta.layout = h->layout; ta.n_envs = h->n_envs; ta.mode = mode; ta.wrapped = h->wrapped;
     ta.sf = h->d_sf; ta.si = h->d_si; ta.car = h->d_car; ta.cam = h->d_cam; ta.pose = h->d_pose;
     ta.act_cc = cc; ta.act_cc64 = cc64; ta.act_man = man; ta.mask = mask; ta.spawn_nodes = spawn;
+    ta.near_x0 = h->near_h.x0; ta.near_y0 = h->near_h.y0; ta.near_inv_cell = h->near_h.inv_cell; ta.near_nx = h->near_h.nx; ta.near_ny = h->near_h.ny;
+    ta.near_off = h->d_near_off; ta.near_edge = h->d_near_edge;
     ta.done = h->ar_done; ta.rng = h->rng; ta.spawn_points = h->spawn_points; ta.n_spawn_points = h->n_spawn_points; ta.last_spawn = h->last_spawn;
     if (outs) ta.out = *outs;
     const int envs_per_block = TC_TRACK_THREADS / 32;

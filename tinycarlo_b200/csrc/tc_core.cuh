@@ -89,6 +89,12 @@ struct TcTrackTables {
     const int32_t *ll_edge_off;  // [C+1]
     const float *ll_nodes32;     // [sumN][2] float copy of ll_nodes for the pre-filter of the nearest-edge scan
     double scan_margin;          // 2*eps of the float pre-filter (metres)
+    // nearest-laneline index (tc_cull.h tc_build_near; global memory, optional): per (class, ground cell) the edges that can
+    // be the arg-min of d(p,n0)+d(p,n1) for a p inside the cell, ascending
+    double near_x0, near_y0, near_inv_cell;
+    int near_nx, near_ny;        // near_nx == 0: no index, scan all edges
+    const int32_t *near_off;     // [C * nx * ny + 1]
+    const uint16_t *near_edge;
 };
 
 // Byte offsets of the sections inside the blob (all multiples of 16); filled by the host at staging.
@@ -119,6 +125,9 @@ TC_HD TcTrackTables tc_track_tables(const unsigned char *base, const TcBlobLayou
     t.ll_edge_off = (const int32_t *)(base + L.off_ll_edge_off);
     t.ll_nodes32 = (const float *)(base + L.off_ll_nodes32);
     t.scan_margin = L.scan_margin;
+    t.near_x0 = t.near_y0 = t.near_inv_cell = 0.0;
+    t.near_nx = t.near_ny = 0;
+    t.near_off = nullptr; t.near_edge = nullptr;
     return t;
 }
 
@@ -220,6 +229,31 @@ TC_HD int tc_nearest_edge_prefiltered(const TcLanes &g, const double *nodes, con
     }
     tc_group_argmin(g, bd, best);
     return best;
+}
+
+// The same arg-min over a candidate list (ascending edge ids) that is known to contain every edge attaining the minimum:
+// the lists of the nearest-laneline index are a few edges long, each lane evaluates at most one or two in float64.
+TC_HD int tc_nearest_edge_list(const TcLanes &g, const double *nodes, const int32_t *edges, const uint16_t *list, int count, double px, double py) {
+    int best = -1;
+    double bd = 0;
+    for (int i = g.lane; i < count; i += g.n) {
+        int e = list[i];
+        int a = edges[2 * e], b = edges[2 * e + 1];
+        double d = fabs(tc_dist(px, py, nodes[2 * a], nodes[2 * a + 1]) + tc_dist(px, py, nodes[2 * b], nodes[2 * b + 1]));
+        if (best < 0 || d < bd) {
+            best = e;
+            bd = d;
+        }
+    }
+    tc_group_argmin(g, bd, best);
+    return best;
+}
+// cell of the nearest-laneline index that holds (x, y), or -1 (no index, outside the grid, NaN)
+TC_HD int tc_near_cell(const TcTrackTables &t, double x, double y) {
+    if (t.near_nx == 0) return -1;
+    double fx = floor((x - t.near_x0) * t.near_inv_cell), fy = floor((y - t.near_y0) * t.near_inv_cell);
+    if (!(fx >= 0 && fx < t.near_nx && fy >= 0 && fy < t.near_ny)) return -1;
+    return (int)fy * t.near_nx + (int)fx;
 }
 
 // ------------------------------------------------------------------------------------------------ car.py
@@ -360,11 +394,16 @@ TC_HD TcInfo tc_get_info(const TcLanes &g, const TcTrackTables &t, const double 
         int a = s.pn[2], b = s.pn[3];
         r.cte = tc_distance_to_edge(s.fx, s.fy, t.lp_nodes[2 * a], t.lp_nodes[2 * a + 1], t.lp_nodes[2 * b], t.lp_nodes[2 * b + 1]);
         r.heading = tc_clip_angle(t.lp_orient[s.pe[1]] - s.rot);
+        const int cell = tc_near_cell(t, s.x, s.y);
         for (int c = 0; c < t.n_classes; c++) {
             const double *nodes = t.ll_nodes + 2 * t.ll_node_off[c];
             const int32_t *edges = t.ll_edges + 2 * t.ll_edge_off[c];
             int m = t.ll_edge_off[c + 1] - t.ll_edge_off[c];
-            int e = tc_nearest_edge_prefiltered(g, nodes, t.ll_nodes32 + 2 * t.ll_node_off[c], edges, m, s.x, s.y, t.scan_margin);
+            int e;
+            if (cell >= 0) {
+                const int32_t *o = t.near_off + (size_t)c * t.near_nx * t.near_ny + cell;
+                e = tc_nearest_edge_list(g, nodes, edges, t.near_edge + o[0], o[1] - o[0], s.x, s.y);
+            } else e = tc_nearest_edge_prefiltered(g, nodes, t.ll_nodes32 + 2 * t.ll_node_off[c], edges, m, s.x, s.y, t.scan_margin);
             nearest[c] = e;
             if (e < 0) continue; // class without edges: the reference would raise on min([])
             int n0 = edges[2 * e], n1 = edges[2 * e + 1];

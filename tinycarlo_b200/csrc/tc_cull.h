@@ -204,3 +204,64 @@ static inline double tc_cull_radius_of(const double *cam /*TC_CAM_N*/, int H, in
     if (!(tx >= 0) || !(ty >= 0)) return -1.0;
     return mr * std::sqrt(1.0 + tx * tx + ty * ty);
 }
+
+// ------------------------------------------------------------------------------------------------ nearest-laneline index
+// car.py:58 asks, per class, for the edge minimising f_e(p) = d(p,n0) + d(p,n1) (layer.py:33-44) - a scan of all edges in the
+// reference and, with a float pre-filter, in the tracking kernel. f_e is 2-Lipschitz in p, so for p in a ground cell with
+// centre c and half diagonal r the arg-min e* obeys f_e*(c) <= f_e*(p) + 2r <= f_min(p) ... <= f_min(c) + 4r: the candidate
+// list of a cell = { e : f_e(c) <= min_e f_e(c) + 4r (+ guard) }, ascending, contains every edge that attains the minimum
+// anywhere in the cell, ties included (the first one wins, as in the reference). Outside the grid the kernel scans all edges.
+struct TcNear {
+    double x0 = 0, y0 = 0, inv_cell = 0;
+    int nx = 0, ny = 0;             // 0: no index
+    std::vector<int32_t> off;       // [C * nx * ny + 1]
+    std::vector<uint16_t> edge;
+    double mean_len = 0.0;
+    int max_len = 0;
+};
+static inline void tc_build_near(const TcMapDesc *map, double pad /* metres around the laneline bounding box */, int max_cells, TcNear &nr) {
+    nr = TcNear();
+    const int C = map->n_classes, n = map->ll_node_off[C];
+    if (n <= 0) return;
+    const double *nodes = map->ll_nodes;
+    for (int i = 0; i < 2 * n; i++) if (!std::isfinite(nodes[i])) return;
+    for (int c = 0; c < C; c++) if (map->ll_edge_off[c + 1] - map->ll_edge_off[c] > 65535) return;
+    double lo[2] = {nodes[0], nodes[1]}, hi[2] = {nodes[0], nodes[1]};
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < 2; j++) { lo[j] = std::min(lo[j], nodes[2 * i + j]); hi[j] = std::max(hi[j], nodes[2 * i + j]); }
+    const double w = hi[0] - lo[0] + 2 * pad, h = hi[1] - lo[1] + 2 * pad;
+    double cell = std::max(0.02, std::sqrt(w * h / std::max(max_cells, 1)));
+    const double fx = std::ceil(w / cell), fy = std::ceil(h / cell);
+    if (!(fx >= 1 && fy >= 1 && fx * fy <= 4.0 * max_cells)) return;
+    nr.x0 = lo[0] - pad; nr.y0 = lo[1] - pad; nr.inv_cell = 1.0 / cell; nr.nx = (int)fx; nr.ny = (int)fy;
+    const double r = cell * 0.70710678118654757 + 1e-9 * (1.0 + std::fabs(nr.x0) + std::fabs(nr.y0) + w + h);   // half diagonal + lookup rounding guard
+    const size_t ncell = (size_t)nr.nx * nr.ny;
+    nr.off.assign((size_t)C * ncell + 1, 0);
+    std::vector<double> f;
+    size_t total = 0;
+    for (int c = 0; c < C; c++) {
+        const double *nd = nodes + 2 * (size_t)map->ll_node_off[c];
+        const int32_t *ed = map->ll_edges + 2 * (size_t)map->ll_edge_off[c];
+        const int m = map->ll_edge_off[c + 1] - map->ll_edge_off[c];
+        f.resize((size_t)std::max(m, 1));
+        for (int iy = 0; iy < nr.ny; iy++)
+            for (int ix = 0; ix < nr.nx; ix++) {
+                const double cx = nr.x0 + (ix + 0.5) * cell, cy = nr.y0 + (iy + 0.5) * cell;
+                double fmin = INFINITY;
+                for (int e = 0; e < m; e++) {
+                    const double *a = nd + 2 * ed[2 * e], *b = nd + 2 * ed[2 * e + 1];
+                    f[e] = std::sqrt((cx - a[0]) * (cx - a[0]) + (cy - a[1]) * (cy - a[1])) + std::sqrt((cx - b[0]) * (cx - b[0]) + (cy - b[1]) * (cy - b[1]));
+                    fmin = std::min(fmin, f[e]);
+                }
+                const double lim = fmin + 4.0 * r + 1e-9 * (1.0 + fmin);
+                int len = 0;
+                for (int e = 0; e < m; e++)
+                    if (f[e] <= lim) { nr.edge.push_back((uint16_t)e); len++; }
+                nr.off[(size_t)c * ncell + (size_t)iy * nr.nx + ix + 1] = len;
+                nr.max_len = std::max(nr.max_len, len);
+                total += len;
+            }
+    }
+    for (size_t i = 0; i < (size_t)C * ncell; i++) nr.off[i + 1] += nr.off[i];
+    nr.mean_len = (double)total / (double)((size_t)C * ncell);
+}

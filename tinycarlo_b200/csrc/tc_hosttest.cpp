@@ -17,6 +17,7 @@
 
 struct HtMap {
     TcPacked pk;
+    TcNear near;   // nearest-laneline index, as tc_create builds it
     std::vector<TcClassTables> cls;
     std::vector<int32_t> edge_off;
     int C, sumE;
@@ -32,15 +33,23 @@ HT_API HtMap *ht_map_create(const TcMapDesc *map) {
     m->sumE = map->ll_edge_off[m->C];
     m->edge_off.assign(map->ll_edge_off, map->ll_edge_off + m->C + 1);
     memcpy(m->colors, map->ll_colors, (size_t)3 * m->C);
+    tc_build_near(map, 1.0, 16384, m->near);
     return m;
 }
 HT_API void ht_map_destroy(HtMap *m) { delete m; }
+
+static void ht_attach_near(const HtMap *m, TcTrackTables &t, bool use) {
+    if (!use || m->near.nx == 0) return;
+    t.near_x0 = m->near.x0; t.near_y0 = m->near.y0; t.near_inv_cell = m->near.inv_cell; t.near_nx = m->near.nx; t.near_ny = m->near.ny;
+    t.near_off = m->near.off.data(); t.near_edge = m->near.edge.data();
+}
 
 // mirrors tc_track_kernel for n envs (mode 0 step / 1 reset)
 HT_API void ht_track(const HtMap *m, int n, int mode, int wrapped, double *sf, int32_t *si, const double *car, const double *cam,
                      double *pose, const float *act_cc, const int32_t *act_man, const uint8_t *mask, const int32_t *spawn,
                      double *info_f64, int32_t *nearest, uint8_t *terminated, uint8_t *truncated) {
     TcTrackTables t = tc_track_tables(m->pk.blob.data(), m->pk.L);
+    ht_attach_near(m, t, true);
     TcLanes g = {0, 1};
     const int C = m->C;
     for (int env = 0; env < n; env++) {
@@ -235,6 +244,49 @@ HT_API void ht_project_culled(const HtMap *m, const HtCull *hc, int n, int H, in
             const int c = edge_cls[e];
             int32_t *s = seg + ((size_t)env * m->sumE + m->edge_off[c] + seg_count[(size_t)env * C + c]++) * 4;
             s[0] = ix[n0]; s[1] = iy[n0]; s[2] = ix[n1]; s[3] = iy[n1];
+        }
+    }
+}
+
+// nearest laneline edge per class for n positions: through the index (use_index != 0, lanes replayed one by one like a
+// group of `nlanes`) or by the plain scan of all edges; cand_len (optional [n]) = candidates looked at in class 0
+HT_API void ht_nearest(const HtMap *m, int n, const double *xy, int use_index, int nlanes, int32_t *out, int32_t *cand_len, double *info3) {
+    TcTrackTables t = tc_track_tables(m->pk.blob.data(), m->pk.L);
+    ht_attach_near(m, t, use_index != 0);
+    if (info3) { info3[0] = (double)m->near.nx * m->near.ny; info3[1] = m->near.mean_len; info3[2] = m->near.max_len; }
+    const int C = m->C;
+    for (int i = 0; i < n; i++) {
+        const double px = xy[2 * i], py = xy[2 * i + 1];
+        const int cell = tc_near_cell(t, px, py);
+        if (cand_len) cand_len[i] = cell >= 0 ? t.near_off[cell + 1] - t.near_off[cell] : -1;
+        for (int c = 0; c < C; c++) {
+            const double *nodes = t.ll_nodes + 2 * t.ll_node_off[c];
+            const int32_t *edges = t.ll_edges + 2 * t.ll_edge_off[c];
+            const int mm = t.ll_edge_off[c + 1] - t.ll_edge_off[c];
+            int best = -1;
+            double bd = 0;
+            for (int lane = 0; lane < (nlanes > 0 ? nlanes : 1); lane++) {   // the group reduction: lexicographic (distance, edge)
+                TcLanes g = {lane, nlanes > 0 ? nlanes : 1};
+                int e;
+                // a one-lane group per replayed lane: the lane's own candidates, no shuffle
+                if (cell >= 0) {
+                    const int32_t *o = t.near_off + (size_t)c * t.near_nx * t.near_ny + cell;
+                    e = -1;
+                    double d_e = 0;
+                    for (int k = g.lane; k < o[1] - o[0]; k += g.n) {
+                        int ee = t.near_edge[o[0] + k];
+                        double d = fabs(tc_dist(px, py, nodes[2 * edges[2 * ee]], nodes[2 * edges[2 * ee] + 1]) +
+                                        tc_dist(px, py, nodes[2 * edges[2 * ee + 1]], nodes[2 * edges[2 * ee + 1] + 1]));
+                        if (e < 0 || d < d_e) { e = ee; d_e = d; }
+                    }
+                    if (e >= 0 && (best < 0 || d_e < bd || (d_e == bd && e < best))) { best = e; bd = d_e; }
+                } else {
+                    TcLanes g1 = {0, 1};
+                    best = tc_nearest_edge(g1, nodes, edges, mm, px, py, nullptr, 0, 0);
+                    break;
+                }
+            }
+            out[(size_t)i * C + c] = best;
         }
     }
 }

@@ -73,6 +73,11 @@ struct TcTrackArgs {
     const int32_t *spawn_points;
     int n_spawn_points;
     int32_t *last_spawn;        // [N] out: lanepath node of the env's most recent reset
+    // nearest-laneline index (global memory; near_nx == 0: none)
+    double near_x0, near_y0, near_inv_cell;
+    int near_nx, near_ny;
+    const int32_t *near_off;
+    const uint16_t *near_edge;
     TcOutputs out;
 };
 
@@ -93,7 +98,9 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS, 3) tc_track_kernel(const TcT
     TcLanes g = {(int)(threadIdx.x & 31), 32};
     tc_mbar_wait(&bar, 0);
     if (env >= a.n_envs) return;
-    const TcTrackTables t = tc_track_tables(smem_blob, a.layout);
+    TcTrackTables t = tc_track_tables(smem_blob, a.layout);
+    t.near_x0 = a.near_x0; t.near_y0 = a.near_y0; t.near_inv_cell = a.near_inv_cell; t.near_nx = a.near_nx; t.near_ny = a.near_ny;
+    t.near_off = a.near_off; t.near_edge = a.near_edge;
     const int C = t.n_classes;
     const double *cp = a.car + (size_t)env * TC_CP_N;
     double *sf = a.sf + (size_t)env * TC_SF_N;
