@@ -85,6 +85,9 @@ struct TcHandle {
     unsigned char *d_cell_blob = nullptr;
     TcCullGrid cull_grid{};
     int env_np = 0, env_max_bytes = 0, env_words = 0;
+    size_t env_smem = 0;     // tc_render_env_kernel (small frames)
+    size_t envb_smem = 0;    // tc_render_env_banded_kernel (large frames, RGB / 1 bit per pixel); 0: not available
+    int envb_rows = 0, envb_bands = 0, envb_words = 0, envb_on = 1;
     double cull_radius = -1.0, cull_mean_nodes = 0.0;
     int cull_cells = 0, cull_max_nodes = 0;
     uint8_t *ar_done = nullptr; // autoreset flags: caller-owned device buffer
@@ -145,8 +148,10 @@ static int tc_install_cull(TcHandle *h, double radius) {
     if (const char *ce = getenv("TC_CULL")) if (atoi(ce) == 0) radius = -1.0;
     tc_build_cull(&m, radius, cell, 0.05, cull);
     const size_t np = tc_env_np(cull.max_nodes, cull.max_edges);
-    const size_t smem = tc_env_smem_bytes(np, cull.max_bytes, h->env_words);
+    const size_t smem = h->fused_all ? tc_env_smem_bytes(np, cull.max_bytes, h->env_words) : 0;
     if (smem > 200 * 1024) return tc_fail(TC_ERR_INVALID, "visible-set tables exceed the shared-memory budget");
+    size_t smem_b = h->fused_all ? 0 : tc_envb_smem_bytes(np, cull.max_bytes, h->C, h->envb_words);
+    if (smem_b > 110 * 1024 || (h->envb_rows * h->W) % 32 != 0 || h->envb_bands > 1024) smem_b = 0;   // not worth it / not word aligned: other paths
     TcCellBlob *dd = nullptr;
     unsigned char *db = nullptr;
     TC_CUDA(cudaMalloc((void **)&dd, cull.desc.size() * sizeof(TcCellBlob)));
@@ -158,7 +163,7 @@ static int tc_install_cull(TcHandle *h, double radius) {
     cudaFree(h->d_cell_desc);
     cudaFree(h->d_cell_blob);
     h->d_cell_desc = dd; h->d_cell_blob = db;
-    h->cull_grid = cull.grid; h->env_np = (int)np; h->env_max_bytes = cull.max_bytes; h->render_smem = smem;
+    h->cull_grid = cull.grid; h->env_np = (int)np; h->env_max_bytes = cull.max_bytes; h->env_smem = smem; h->envb_smem = smem_b;
     h->cull_radius = cull.radius; h->cull_mean_nodes = cull.mean_nodes; h->cull_cells = (int)cull.desc.size(); h->cull_max_nodes = cull.max_nodes;
     return TC_OK;
 }
@@ -322,14 +327,22 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
         h->fused_cblob = h->max_cblob_bytes; h->fused_words = h->plane_words_full;
         h->render_smem = smem_one;
         h->env_words = words_all;
+        {
+            size_t eb = 30 * 1024;   // C band planes + their OR; with 24*np and the primitive slots of 48 segments: 4 blocks per SM on Knuffingen
+            if (const char *kb = getenv("TC_ENVB_PLANE_KB")) eb = (size_t)std::max(4, atoi(kb)) * 1024;
+            tc_band_geometry(h->H, h->W, C + 1, eb, &h->envb_rows, &h->envb_bands, &h->envb_words);
+            if (const char *on = getenv("TC_ENV_BANDED")) h->envb_on = atoi(on) != 0;
+        }
         h->fused_ok = all || smem_one <= 56 * 1024; // >= 4 blocks per SM; larger frames take the banded two-kernel path
-        if (all) TC_TRYH(tc_install_cull(h, -1.0));   // the whole graph until the camera parameters are known
+        TC_TRYH(tc_install_cull(h, -1.0));   // the whole graph until the camera parameters are known
     }
-    if (h->fused_ok) {
-        if (const char *rt = getenv("TC_RENDER_THREADS")) h->render_threads = atoi(rt) == 128 ? 128 : 256;
 #define TC_PREP_RENDER(K)                 \
     TC_CUDAH(tc_allow_max_smem(K));       \
     TC_CUDAH(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+    TC_PREP_RENDER((tc_render_env_banded_kernel<TC_FMT_RGB>));
+    TC_PREP_RENDER((tc_render_env_banded_kernel<TC_FMT_BITS>));
+    if (h->fused_ok) {
+        if (const char *rt = getenv("TC_RENDER_THREADS")) h->render_threads = atoi(rt) == 128 ? 128 : 256;
         TC_PREP_RENDER((tc_render_env_kernel<128, TC_FMT_U8>));
         TC_PREP_RENDER((tc_render_env_kernel<256, TC_FMT_U8>));
         TC_PREP_RENDER((tc_render_env_kernel<256, TC_FMT_RGB>));
@@ -338,8 +351,8 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
         TC_PREP_RENDER((tc_render_classes_kernel<256, TC_FMT_U8>));
         TC_PREP_RENDER((tc_render_classes_kernel<256, TC_FMT_BITS>));
         TC_PREP_RENDER((tc_render_classes_kernel<256, TC_FMT_BF16>));
-#undef TC_PREP_RENDER
     }
+#undef TC_PREP_RENDER
     TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_rgb_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -367,7 +380,7 @@ int tc_set_camera_params(TcHandle *h, const double *dev_cam, const int32_t *dev_
     TC_CUDA(cudaMemcpyAsync(h->d_cam, dev_cam, (size_t)h->n_envs * TC_CAM_N * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     TC_CUDA(cudaMemcpyAsync(h->d_thick, dev_thickness, (size_t)h->n_envs * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     h->cam_set = true;
-    if (h->fused_all) {
+    if (h->fused_all || h->envb_smem > 0 || h->cull_radius >= 0) {
         // the visible-set tables depend on how far the cameras see: read the rows back (this call synchronises) and rebuild
         std::vector<double> rows((size_t)h->n_envs * TC_CAM_N);
         TC_CUDA(cudaMemcpyAsync(rows.data(), h->d_cam, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -407,7 +420,8 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
                             cudaStream_t st, cudaEvent_t after_project = nullptr) {
     const int N = h->n_envs, C = h->C;
     if (obs_format == TC_OBS_CLASSES_BITS || obs_format == TC_OBS_CLASSES_BF16) {
-        if (!h->fused_ok || seg_count_out || seg_out) return tc_fail(TC_ERR_INVALID, "bit-packed / bf16 observations need the fused render path (frame too large or debug segments requested)");
+        const bool banded = obs_format == TC_OBS_CLASSES_BITS && !h->fused_all && h->envb_on && h->envb_smem > 0;
+        if ((!h->fused_ok && !banded) || seg_count_out || seg_out) return tc_fail(TC_ERR_INVALID, "bit-packed / bf16 observations need the fused render path (frame too large or debug segments requested)");
         if (obs_format == TC_OBS_CLASSES_BF16 && (h->H * h->W) % 8 != 0) return tc_fail(TC_ERR_INVALID, "bf16 observations need H*W to be a multiple of 8");
         if (obs_format == TC_OBS_CLASSES_BITS && h->fused_all && (h->H * h->W) % 32 != 0) return tc_fail(TC_ERR_INVALID, "bit-packed observations of small frames need H*W to be a multiple of 32");
     }
@@ -419,12 +433,28 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
         memcpy(ea.colors, h->colors, sizeof(ea.colors));
         ea.timeline = mask ? nullptr : h->timeline;
         if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
-        const size_t sm = h->render_smem;
+        const size_t sm = h->env_smem;
         if (obs_format == TC_OBS_RGB) tc_render_env_kernel<256, TC_FMT_RGB><<<N, 256, sm, st>>>(ea);
         else if (obs_format == TC_OBS_CLASSES_BITS) tc_render_env_kernel<256, TC_FMT_BITS><<<N, 256, sm, st>>>(ea);
         else if (obs_format == TC_OBS_CLASSES_BF16) tc_render_env_kernel<256, TC_FMT_BF16><<<N, 256, sm, st>>>(ea);
         else if (h->render_threads == 128) tc_render_env_kernel<128, TC_FMT_U8><<<N, 128, sm, st>>>(ea);
         else tc_render_env_kernel<256, TC_FMT_U8><<<N, 256, sm, st>>>(ea);
+        h->launches++;
+        TC_CUDA(cudaGetLastError());
+        return TC_OK;
+    }
+    if (obs && !h->fused_all && h->envb_on && h->envb_smem > 0 && !seg_count_out && !seg_out && (obs_format == TC_OBS_RGB || obs_format == TC_OBS_CLASSES_BITS)) {
+        // large frames whose stores are not the bound: a block per env, bands walked inside the block
+        TcRenderEnvArgs ea;
+        ea.cell_desc = h->d_cell_desc; ea.cell_blob = h->d_cell_blob; ea.grid = h->cull_grid; ea.n_envs = N; ea.n_classes = C;
+        ea.np = h->env_np; ea.max_bytes = h->env_max_bytes; ea.H = h->H; ea.W = h->W; ea.plane_words = 0;
+        ea.pose = h->d_pose; ea.cam = h->d_cam; ea.thickness = h->d_thick; ea.mask = mask; ea.obs = obs;
+        memcpy(ea.colors, h->colors, sizeof(ea.colors));
+        ea.timeline = nullptr;
+        ea.rows_per_band = h->envb_rows; ea.n_bands = h->envb_bands; ea.band_words = h->envb_words;
+        if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
+        if (obs_format == TC_OBS_RGB) tc_render_env_banded_kernel<TC_FMT_RGB><<<N, 256, h->envb_smem, st>>>(ea);
+        else tc_render_env_banded_kernel<TC_FMT_BITS><<<N, 256, h->envb_smem, st>>>(ea);
         h->launches++;
         TC_CUDA(cudaGetLastError());
         return TC_OK;
@@ -615,7 +645,7 @@ int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline) {
 
 int tc_debug_cull_info(TcHandle *h, double *out4) {
     if (!h || !out4) return tc_fail(TC_ERR_INVALID, "tc_debug_cull_info: null argument");
-    out4[0] = h->fused_all ? h->cull_radius : -2.0; out4[1] = h->cull_cells; out4[2] = h->cull_mean_nodes; out4[3] = h->cull_max_nodes;
+    out4[0] = (h->fused_all || h->envb_smem > 0) ? h->cull_radius : -2.0; out4[1] = h->cull_cells; out4[2] = h->cull_mean_nodes; out4[3] = h->cull_max_nodes;
     return TC_OK;
 }
 

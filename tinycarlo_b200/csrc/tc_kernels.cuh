@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const 
 // zero the C band planes, draw the primitives that can touch the band, OR the planes, compose and stream the rows out.
 // Frames with more than TC_RGBE_MAX_SEGS visible segments (the list does not fit) redo the set-up per band in rounds.
 // shared memory: [C band planes + pad][OR plane + pad][primitive slots of TC_RGBE_MAX_SEGS segments][per-segment class, row range]
-#define TC_RGBE_MAX_SEGS 64
+#define TC_RGBE_MAX_SEGS 48
 __host__ __device__ inline size_t tc_rgbe_off_prims(int C, int plane_words) { return tc_raster_rgb_planes_bytes(C, plane_words) + tc_raster_rgb_any_bytes(plane_words); }
 __host__ __device__ inline size_t tc_rgbe_smem_bytes(int C, int plane_words) {
     return tc_rgbe_off_prims(C, plane_words) + (((size_t)TC_RGBE_MAX_SEGS * TC_ENV_SEG_WORDS * 4 + 15) & ~(size_t)15);
@@ -959,6 +959,7 @@ struct TcRenderEnvArgs {
     uint8_t *obs;
     uint8_t colors[TC_MAX_CLASSES * 3];
     long long *timeline;       // optional debug [N][10], see tools/timeline.py
+    int rows_per_band, n_bands, band_words;   // banded variant (large frames): rows per band, bands, words of one class's band plane (incl. pad word)
 };
 // shared memory: phase 1 [Px Py Pz | ix iy | 5 flag arrays | cell tables (TMA)]; phase 2 [segments + classes | plane | primitive slots]
 __host__ __device__ inline size_t tc_env_np(int max_nodes, int max_edges) {
@@ -1146,6 +1147,201 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRe
     }
 #endif
 #undef TC_TL
+}
+
+// ------------------------------------------------------------------------------------------------ fused, block per env, banded
+// Large frames in the formats whose stores are NOT the bound - RGB (composition work per byte) and 1 bit per pixel (8x fewer
+// bytes): a block owns a whole frame. Camera pass on the visible-set sub-graph as in tc_render_env_kernel, set-up of all
+// segments once, then the row bands one after the other: zero the C band planes, draw the primitives that can touch the band
+// (compact list built by all threads), store. (u8 and bf16 large frames stay with the per-class kernel, which streams at the
+// HBM write ceiling.)
+// shared memory: phase 1 as tc_render_env_kernel; phase 2 [segments + classes | C band planes + pad | OR plane + pad | primitive slots]
+__host__ __device__ inline size_t tc_envb_off_any(size_t np, int C, int band_words) { return np * 24 + tc_raster_rgb_planes_bytes(C, band_words); }
+__host__ __device__ inline size_t tc_envb_off_prims(size_t np, int C, int band_words) { return tc_envb_off_any(np, C, band_words) + tc_raster_rgb_any_bytes(band_words); }
+__host__ __device__ inline size_t tc_envb_smem_bytes(size_t np, int max_bytes, int C, int band_words) {
+    size_t a = tc_env_off_tables(np) + (size_t)max_bytes;
+    size_t b = tc_envb_off_prims(np, C, band_words) + (((size_t)TC_RGBE_MAX_SEGS * TC_ENV_SEG_WORDS * 4 + 15) & ~(size_t)15);
+    return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256, 4) tc_render_env_banded_kernel(const TcRenderEnvArgs a) {
+    constexpr int NT = 256;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int seg_cnt;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double s_pose[12], s_cam[TC_CAM_N];
+    __shared__ uint32_t s_color24[TC_MAX_CLASSES];
+    __shared__ TcCellBlob s_desc;
+    __shared__ int seg_lo[TC_RGBE_MAX_SEGS], seg_hi[TC_RGBE_MAX_SEGS];
+    __shared__ uint16_t list[TC_RGBE_MAX_SEGS * TC_MAX_PRIMS_PER_SEG];
+    __shared__ int list_n;
+    __shared__ unsigned band_mask;
+    const int env = blockIdx.x;
+    if (a.mask && !a.mask[env]) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C = a.n_classes;
+    const size_t np = (size_t)a.np;
+    unsigned char *tab_smem = smem_raw + tc_env_off_tables(np);
+    if (tid == 0) {
+        const TcCellBlob d = a.cell_desc[tc_cull_cell(a.grid, a.pose + (size_t)env * 12)];
+        seg_cnt = 0;
+        tc_mbar_init(&bar, 1);
+        tc_fence_mbar_init();
+        if (d.bytes > 0) {
+            tc_mbar_expect_tx(&bar, (uint32_t)d.bytes);
+            tc_bulk_g2s(tab_smem, a.cell_blob + d.offset, (uint32_t)d.bytes, &bar);
+        }
+        s_desc = d;
+    }
+    if (FMT == TC_FMT_RGB && tid >= 64 && tid < 64 + TC_MAX_CLASSES) s_color24[tid - 64] = tc_color24_of(a.colors, tid - 64);
+    if (tid >= 32 && tid < 44) s_pose[tid - 32] = a.pose[(size_t)env * 12 + tid - 32];
+    else if (tid >= 44 && tid < 44 + (TC_CAM_MAX_RANGE - TC_CAM_FX + 1)) s_cam[TC_CAM_FX + tid - 44] = a.cam[(size_t)env * TC_CAM_N + TC_CAM_FX + tid - 44];
+    __syncthreads();
+    const int n = s_desc.n_nodes, m = s_desc.n_edges;
+    int4 *segs = (int4 *)smem_raw;
+    uint32_t *planes = (uint32_t *)(smem_raw + np * 24);
+    uint32_t *any_plane = (uint32_t *)(smem_raw + tc_envb_off_any(np, C, a.band_words));
+    int32_t *pw = (int32_t *)(smem_raw + tc_envb_off_prims(np, C, a.band_words));
+    if (n > 0) {
+        // ---- camera pass (camera.py:52-110) on the cell's sub-graph, exactly as in tc_render_env_kernel
+        TcProjScratch sc;
+        sc.Px = (double *)smem_raw; sc.Py = sc.Px + np; sc.Pz = sc.Py + np;
+        sc.ix = (int32_t *)(sc.Pz + np); sc.iy = sc.ix + np;
+        uint8_t *fA = (uint8_t *)(sc.iy + np), *fB = fA + np, *rA = fB + np, *rB = rA + np;
+        sc.vis = rB + np; sc.front = fA; sc.inr = rA;
+        const double *pose = s_pose, *cam = s_cam;
+        const double max_range = cam[TC_CAM_MAX_RANGE];
+        tc_mbar_wait(&bar, 0);
+        const TcClassTables ct = tc_class_tables_from_cell(tab_smem, s_desc);
+        const uint8_t *core = tab_smem + s_desc.off_core, *edge_cls = tab_smem + s_desc.off_edge_cls;
+        for (int v = tid; v < n; v += NT) {
+            double X, Y, Z;
+            tc_transform_node(pose, ct.nodes[2 * v], ct.nodes[2 * v + 1], X, Y, Z);
+            sc.Px[v] = X; sc.Py[v] = Y; sc.Pz[v] = Z;
+            fA[v] = Z < 0;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 4; pass++) {
+            const bool range = pass >= 2, outgoing = (pass & 1) == 0;
+            const double tz = range ? -max_range : -0.0000001;
+            uint8_t *src = range ? (outgoing ? rA : rB) : (outgoing ? fA : fB), *dst = range ? (outgoing ? rB : rA) : (outgoing ? fB : fA);
+            if (pass == 2) {
+                for (int v = tid; v < n; v += NT) rA[v] = sc.Pz[v] > -max_range;
+                __syncthreads();
+            }
+            for (int v = tid; v < n; v += NT) dst[v] = src[v] | (uint8_t)tc_clip_pass_node(ct, sc, src, v, outgoing, tz);
+            __syncthreads();
+        }
+        for (int v = tid; v < n; v += NT) {
+            double u, w;
+            tc_project(cam, sc.Px[v], sc.Py[v], sc.Pz[v], u, w);
+            sc.ix[v] = tc_np_int32(u);
+            sc.iy[v] = tc_np_int32(w);
+            sc.vis[v] = (core[v] && u > 0 && u < a.W && w > 0 && w < a.H && fA[v] && rA[v]) ? 1 : 0;
+        }
+        __syncthreads();
+        uint8_t *seg_cls_w = (uint8_t *)(segs + m);
+        for (int e = tid; e < m; e += NT) {
+            int n0 = ct.edges[2 * e], n1 = ct.edges[2 * e + 1];
+            if (sc.vis[n0] || sc.vis[n1]) {
+                int slot = atomicAdd(&seg_cnt, 1);
+                segs[slot] = make_int4(sc.ix[n0], sc.iy[n0], sc.ix[n1], sc.iy[n1]);
+                seg_cls_w[slot] = edge_cls[e];
+            }
+        }
+        __syncthreads();
+    }
+    const int total = seg_cnt;
+    const uint8_t *seg_cls = (const uint8_t *)(segs + m);
+    const int t = a.thickness[env];
+    const TcLanes g = {lane, 32};
+    // ---- rasteriser: set-up once (or, for more than TC_RGBE_MAX_SEGS segments, per band in rounds), bands in turn
+    auto setup = [&](int first, int cnt) {
+        if (tid == 0) band_mask = 0;
+        for (int i = tid; i < cnt * TC_MAX_PRIMS_PER_SEG; i += NT)
+            pw[(i / TC_MAX_PRIMS_PER_SEG) * TC_ENV_SEG_WORDS + (i % TC_MAX_PRIMS_PER_SEG) * 8] = TC_PRIM_NONE;
+        __syncthreads();
+        for (int sub = 0; sub < cnt; sub += 32) {
+            const int sl = sub + lane;
+            if (sl < cnt) {
+                const int4 s4 = segs[first + sl];
+                if (warp == 7) {   // (the role warps are 0..5) every primitive of a segment stays within t + 2 rows of its end points
+                    const long long lo = (long long)min(s4.y, s4.w) - t - 2, hi = (long long)max(s4.y, s4.w) + t + 2;
+                    const int ilo = (int)max(lo, (long long)-1), ihi = (int)min(hi, (long long)a.H);
+                    seg_lo[sl] = ilo; seg_hi[sl] = ihi;
+                    if (ihi >= 0 && ilo < a.H) {
+                        const int b0 = max(ilo, 0) / a.rows_per_band, b1 = min(ihi, a.H - 1) / a.rows_per_band;
+                        unsigned mk = a.n_bands > 32 ? 0xffffffffu : 0u;
+                        for (int b = b0; b <= b1 && a.n_bands <= 32; b++) mk |= 1u << b;
+                        atomicOr(&band_mask, mk);
+                    }
+                }
+                for (int role = warp; role < TC_N_ROLES; role += NT / 32)
+                    tc_polyline_setup<true>(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, role, (TcPrim *)(pw + sl * TC_ENV_SEG_WORDS));
+            }
+        }
+        __syncthreads();
+    };
+    auto draw = [&](int first, int cnt, int y_lo, int y_hi) {
+        if (tid == 0) list_n = 0;
+        __syncthreads();
+        for (int p = tid; p < cnt * TC_MAX_PRIMS_PER_SEG; p += NT) {
+            const int sl = p / TC_MAX_PRIMS_PER_SEG;
+            if (seg_hi[sl] < y_lo || seg_lo[sl] >= y_hi) continue;
+            if (pw[sl * TC_ENV_SEG_WORDS + (p % TC_MAX_PRIMS_PER_SEG) * 8] == TC_PRIM_NONE) continue;
+            list[atomicAdd(&list_n, 1)] = (uint16_t)p;
+        }
+        __syncthreads();
+        const int ln = list_n;
+        for (int i = warp; i < ln; i += NT / 32) {
+            const int p = list[i], sl = p / TC_MAX_PRIMS_PER_SEG;
+            const TcPrim &q = *(const TcPrim *)(pw + sl * TC_ENV_SEG_WORDS + (p % TC_MAX_PRIMS_PER_SEG) * 8);
+            TcPlane pl = {planes + (size_t)seg_cls[first + sl] * a.band_words, a.H, a.W, y_lo, y_hi, y_lo};
+            tc_prim_draw(g, pl, q);
+        }
+    };
+    const bool once = total <= TC_RGBE_MAX_SEGS;
+    if (once && total > 0) setup(0, total);
+    const size_t frame_words = ((size_t)a.H * a.W + 31) / 32;
+    for (int band = 0; band < a.n_bands; band++) {
+        const int y_lo = band * a.rows_per_band;
+        const int y_hi = min(a.H, y_lo + a.rows_per_band);
+        const bool drew = once ? (total > 0 && ((band_mask >> (band & 31)) & 1u)) : total > 0;
+        if (drew) {
+            for (int i = tid; i < C * a.band_words + 1; i += NT) planes[i] = 0;
+            __syncthreads();
+            if (once) draw(0, total, y_lo, y_hi);
+            else
+                for (int first = 0; first < total; first += TC_RGBE_MAX_SEGS) {
+                    const int cnt = min(TC_RGBE_MAX_SEGS, total - first);
+                    setup(first, cnt);
+                    draw(first, cnt, y_lo, y_hi);
+                    __syncthreads();
+                }
+            __syncthreads();
+            if (FMT == TC_FMT_RGB) {
+                for (int i = tid; i <= a.band_words; i += NT) {
+                    uint32_t v = 0;
+                    if (i < a.band_words)
+                        for (int c = 0; c < C; c++) v |= planes[(size_t)c * a.band_words + i];
+                    any_plane[i] = v;
+                }
+                __syncthreads();
+            }
+        }
+        if (FMT == TC_FMT_RGB)
+            tc_store_rgb<NT>(a.obs + ((size_t)env * a.H + y_lo) * a.W * 3, (uint32_t)((y_hi - y_lo) * a.W), planes, (uint32_t)a.band_words * 32u, C,
+                             s_color24, drew, any_plane);
+        else {
+            // 1 bit per pixel: the band planes are the output (the host guarantees rows_per_band * W % 32 == 0)
+            const int words = (int)(((size_t)(y_hi - y_lo) * a.W + 31) / 32);
+            uint32_t *o = (uint32_t *)a.obs + (size_t)env * C * frame_words + ((size_t)y_lo * a.W) / 32;
+            for (int c = 0; c < C; c++)
+                for (int i = tid; i < words; i += NT) o[(size_t)c * frame_words + i] = drew ? planes[(size_t)c * a.band_words + i] : 0u;
+        }
+        __syncthreads();   // the next band reuses the planes
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ blob noise
