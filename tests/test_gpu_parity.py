@@ -523,3 +523,38 @@ def test_cuda_step_is_graph_capturable():
             assert torch.equal(envs[0].done_flags, envs[1].done_flags)
     for e in envs:
         e.close()
+
+
+@pytest.mark.parametrize("thickness", [2, 1])
+def test_cuda_banded_env_kernel_with_many_segments(thickness):
+    """Large RGB / bit-packed frames go through the banded block-per-env kernel. With a long camera range a frame shows more
+    segments than the kernel keeps set up at once (48): the per-band rounds must give the oracle's frames too. Thickness 1
+    exercises the Bresenham primitives in bands."""
+    n, steps = 48, 8
+    cam = {"resolution": [480, 640], "max_range": 3.0, "orientation": [30, 0, 0], "line_thickness": thickness}
+    cfg_rgb = make_config("simple_layout", "rgb", cam=cam, car={"max_velocity": 0.15})
+    cfg_cls = make_config("simple_layout", "classes", cam=cam, car={"max_velocity": 0.15})
+    env_rgb, env_bits = _vec(cfg_rgb, n), _vec(cfg_cls, n, obs_format="classes_bits")
+    env_seg = _vec(cfg_cls, n, debug_segments=True)      # unfused path: exports the segment counts
+    o_rgb, o_cls = oracle_env(cfg_rgb, n), oracle_env(cfg_cls, n)
+    rng = np.random.default_rng(3)
+    for e in (env_rgb, env_bits, env_seg):
+        e.reset(seed=6)
+    for o in (o_rgb, o_cls):
+        o.reset(env_rgb._spawn_nodes.cpu().numpy())
+    most = 0
+    for t in range(steps):
+        cc = np.stack([rng.uniform(0.3, 1, n), rng.uniform(-1, 1, n)], 1).astype(np.float32)
+        man = rng.integers(0, 4, n).astype(np.int32)
+        for e in (env_rgb, env_bits, env_seg):
+            e.step({"car_control": torch.from_numpy(cc).cuda(), "maneuver": torch.from_numpy(man).cuda()})
+        for o in (o_rgb, o_cls):
+            o.step(cc.astype(np.float64), man)
+        assert np.array_equal(env_rgb.obs.cpu().numpy(), o_rgb.obs), ("rgb", t)
+        words = env_bits.obs.cpu().numpy().view(np.uint32)
+        bits = np.unpackbits(words.view(np.uint8), axis=-1, bitorder="little")[..., : 480 * 640].reshape(n, -1, 480, 640)
+        assert np.array_equal(bits * 255, o_cls.obs), ("bits", t)
+        most = max(most, int(env_seg.out["seg_count"].sum(1).max()))
+    assert most > 48, most
+    for e in (env_rgb, env_bits, env_seg):
+        e.close()

@@ -62,8 +62,6 @@ struct TcHandle {
     // raster launch geometry
     int rows_per_band_cls = 0, n_bands_cls = 0, plane_words_cls = 0;
     int rows_per_band_rgb = 0, n_bands_rgb = 0, plane_words_rgb = 0;
-    int rows_per_band_rgbe = 0, n_bands_rgbe = 0, plane_words_rgbe = 0; // block-per-env RGB kernel (large frames)
-    int rgb_env = 1;
     size_t track_smem = 0, proj_smem = 0, render_smem = 0;
     int max_edges = 0, plane_words_full = 0;
     int stagger_ns = 0, n_sms = 148;
@@ -298,10 +296,6 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
         size_t rgb_budget = 64 * 1024;   // measured on 480x640: 24/32/40/48/64/96 KB -> 3.02/2.64/2.64/2.49/2.32/4.84 ms per 8192 envs
         if (const char *kb = getenv("TC_RGB_PLANE_KB")) rgb_budget = (size_t)std::max(4, atoi(kb)) * 1024;
         tc_band_geometry(h->H, h->W, C, rgb_budget, &h->rows_per_band_rgb, &h->n_bands_rgb, &h->plane_words_rgb);
-        size_t rgbe_budget = 30 * 1024;   // C planes + their OR; with the primitive slots of 64 segments: 4 blocks per SM
-        if (const char *kb = getenv("TC_RGBE_PLANE_KB")) rgbe_budget = (size_t)std::max(4, atoi(kb)) * 1024;
-        tc_band_geometry(h->H, h->W, C + 1, rgbe_budget, &h->rows_per_band_rgbe, &h->n_bands_rgbe, &h->plane_words_rgbe);
-        if (const char *re = getenv("TC_RGB_ENV")) h->rgb_env = atoi(re) != 0;
     }
     for (int c = 0; c < C; c++) h->max_edges = std::max(h->max_edges, map->ll_edge_off[c + 1] - map->ll_edge_off[c]);
     {
@@ -360,8 +354,6 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     TC_CUDAH(tc_allow_max_smem(tc_project_kernel));
     TC_CUDAH(tc_allow_max_smem(tc_raster_classes_kernel));
     TC_CUDAH(tc_allow_max_smem(tc_raster_rgb_kernel));
-    TC_CUDAH(cudaFuncSetAttribute(tc_raster_rgb_env_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    TC_CUDAH(tc_allow_max_smem(tc_raster_rgb_env_kernel));
     *out = h;
     return TC_OK;
 }
@@ -498,13 +490,8 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
         ra.rows_per_band = h->rows_per_band_cls; ra.n_bands = h->n_bands_cls; ra.plane_words = h->plane_words_cls;
         tc_raster_classes_kernel<<<N * C * ra.n_bands, TC_RASTER_THREADS, (size_t)ra.plane_words * 4, st>>>(ra);
     } else {
-        if (h->rgb_env) {
-            ra.rows_per_band = h->rows_per_band_rgbe; ra.n_bands = h->n_bands_rgbe; ra.plane_words = h->plane_words_rgbe;
-            tc_raster_rgb_env_kernel<<<N, TC_RASTER_THREADS, tc_rgbe_smem_bytes(C, ra.plane_words), st>>>(ra);
-        } else {
-            ra.rows_per_band = h->rows_per_band_rgb; ra.n_bands = h->n_bands_rgb; ra.plane_words = h->plane_words_rgb;
-            tc_raster_rgb_kernel<<<N * ra.n_bands, TC_RASTER_THREADS, tc_raster_rgb_smem_bytes(C, ra.plane_words), st>>>(ra);
-        }
+        ra.rows_per_band = h->rows_per_band_rgb; ra.n_bands = h->n_bands_rgb; ra.plane_words = h->plane_words_rgb;
+        tc_raster_rgb_kernel<<<N * ra.n_bands, TC_RASTER_THREADS, tc_raster_rgb_smem_bytes(C, ra.plane_words), st>>>(ra);
     }
     h->launches++;
     TC_CUDA(cudaGetLastError());

@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_classes_kernel(co
 
 // rgb, large frames: grid = N*n_bands blocks; C class planes of the band; later classes overwrite earlier ones
 // (renderer.py:41-43). Segments come from tc_project_kernel; set-up is split by role over the warps like in the fused kernel.
+// (Fallback of tc_render_env_banded_kernel, which sets a frame's segments up once instead of once per band.)
 // shared memory: [C class planes + pad word][OR of the class planes + pad word][primitive slots]
 __host__ __device__ inline size_t tc_raster_rgb_planes_bytes(int C, int plane_words) { return (((size_t)C * plane_words + 1) * 4 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t tc_raster_rgb_any_bytes(int plane_words) { return (((size_t)plane_words + 1) * 4 + 15) & ~(size_t)15; }
@@ -597,122 +598,7 @@ __global__ void __launch_bounds__(TC_RASTER_THREADS) tc_raster_rgb_kernel(const 
     tc_store_rgb<TC_RASTER_THREADS>(out, (uint32_t)((y_hi - y_lo) * a.W), planes, (uint32_t)a.plane_words * 32u, C, color24, drew, any_plane);
 }
 
-// rgb, large frames, block per env: the polyline set-up is the latency-bound part of a band block, and a segment that
-// crosses several bands used to be set up in each of them. Here a block owns a whole frame: it sets up all segments of the
-// env ONCE (rounds of 32, lane = segment, warp = role, primitives kept in shared memory) and then walks the row bands -
-// zero the C band planes, draw the primitives that can touch the band, OR the planes, compose and stream the rows out.
-// Frames with more than TC_RGBE_MAX_SEGS visible segments (the list does not fit) redo the set-up per band in rounds.
-// shared memory: [C band planes + pad][OR plane + pad][primitive slots of TC_RGBE_MAX_SEGS segments][per-segment class, row range]
-#define TC_RGBE_MAX_SEGS 48
-__host__ __device__ inline size_t tc_rgbe_off_prims(int C, int plane_words) { return tc_raster_rgb_planes_bytes(C, plane_words) + tc_raster_rgb_any_bytes(plane_words); }
-__host__ __device__ inline size_t tc_rgbe_smem_bytes(int C, int plane_words) {
-    return tc_rgbe_off_prims(C, plane_words) + (((size_t)TC_RGBE_MAX_SEGS * TC_ENV_SEG_WORDS * 4 + 15) & ~(size_t)15);
-}
-__global__ void __launch_bounds__(TC_RASTER_THREADS, 4) tc_raster_rgb_env_kernel(const TcRasterArgs a) {
-    extern __shared__ __align__(16) uint32_t planes[];
-    __shared__ uint32_t color24[TC_MAX_CLASSES];
-    __shared__ int cls_cnt[TC_MAX_CLASSES];
-    __shared__ int seg_c[TC_RGBE_MAX_SEGS], seg_lo[TC_RGBE_MAX_SEGS], seg_hi[TC_RGBE_MAX_SEGS];
-    __shared__ uint16_t list[TC_RGBE_MAX_SEGS * TC_MAX_PRIMS_PER_SEG];
-    __shared__ int list_n;
-    __shared__ unsigned band_mask;   // bit b: some segment of the current slots can touch band b (n_bands <= 32, else all ones)
-    const int C = a.n_classes;
-    const int env = blockIdx.x;
-    if (a.mask && !a.mask[env]) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < TC_MAX_CLASSES) {
-        color24[tid] = tc_color24_of(a.colors, tid);
-        cls_cnt[tid] = tid < C ? a.seg_count[(size_t)env * C + tid] : 0;
-    }
-    __syncthreads();
-    int total = 0;
-    for (int c = 0; c < C; c++) total += cls_cnt[c];
-    const int t = a.thickness[env];
-    uint32_t *any_plane = (uint32_t *)((unsigned char *)planes + tc_raster_rgb_planes_bytes(C, a.plane_words));
-    int32_t *pw = (int32_t *)((unsigned char *)planes + tc_rgbe_off_prims(C, a.plane_words));
-    const TcLanes g = {lane, 32};
-    // set-up of the segments [first, first + n) of the env (n <= TC_RGBE_MAX_SEGS) into the primitive slots
-    auto setup = [&](int first, int n) {
-        if (tid == 0) band_mask = 0;
-        for (int i = tid; i < n * TC_MAX_PRIMS_PER_SEG; i += TC_RASTER_THREADS)
-            pw[(i / TC_MAX_PRIMS_PER_SEG) * TC_ENV_SEG_WORDS + (i % TC_MAX_PRIMS_PER_SEG) * 8] = TC_PRIM_NONE;
-        __syncthreads();
-        for (int sub = 0; sub < n; sub += 32) {
-            const int sl = sub + lane;
-            if (sl < n) {
-                int k = first + sl, c = 0;
-                while (k >= cls_cnt[c]) { k -= cls_cnt[c]; c++; }
-                const int4 s4 = *(const int4 *)(a.seg + ((size_t)env * a.sum_edges + a.edge_off[c] + k) * 4);
-                if (warp == 0) {
-                    seg_c[sl] = c;
-                    // every primitive of a segment stays within t + 2 rows of its end points
-                    const long long lo = (long long)min(s4.y, s4.w) - t - 2, hi = (long long)max(s4.y, s4.w) + t + 2;
-                    const int ilo = (int)max(lo, (long long)-1), ihi = (int)min(hi, (long long)a.H);
-                    seg_lo[sl] = ilo; seg_hi[sl] = ihi;
-                    if (ihi >= 0 && ilo < a.H) {
-                        const int b0 = max(ilo, 0) / a.rows_per_band, b1 = min(ihi, a.H - 1) / a.rows_per_band;
-                        unsigned mk = a.n_bands > 32 ? 0xffffffffu : 0u;
-                        for (int b = b0; b <= b1 && a.n_bands <= 32; b++) mk |= 1u << b;
-                        atomicOr(&band_mask, mk);
-                    }
-                }
-                for (int role = warp; role < TC_N_ROLES; role += TC_RASTER_THREADS / 32)
-                    tc_polyline_setup<true>(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, role, (TcPrim *)(pw + sl * TC_ENV_SEG_WORDS));
-            }
-        }
-        __syncthreads();
-    };
-    // the primitives of the current slots that can touch rows [y_lo, y_hi): found by all threads at once (one primitive
-    // each), listed in shared memory, then drawn warp by warp
-    auto draw = [&](int n, int y_lo, int y_hi) {
-        if (tid == 0) list_n = 0;
-        __syncthreads();
-        for (int p = tid; p < n * TC_MAX_PRIMS_PER_SEG; p += TC_RASTER_THREADS) {
-            const int sl = p / TC_MAX_PRIMS_PER_SEG;
-            if (seg_hi[sl] < y_lo || seg_lo[sl] >= y_hi) continue;
-            if (pw[sl * TC_ENV_SEG_WORDS + (p % TC_MAX_PRIMS_PER_SEG) * 8] == TC_PRIM_NONE) continue;
-            list[atomicAdd(&list_n, 1)] = (uint16_t)p;
-        }
-        __syncthreads();
-        const int m = list_n;
-        for (int i = warp; i < m; i += TC_RASTER_THREADS / 32) {
-            const int p = list[i], sl = p / TC_MAX_PRIMS_PER_SEG;
-            const TcPrim &q = *(const TcPrim *)(pw + sl * TC_ENV_SEG_WORDS + (p % TC_MAX_PRIMS_PER_SEG) * 8);
-            TcPlane pl = {planes + (size_t)seg_c[sl] * a.plane_words, a.H, a.W, y_lo, y_hi, y_lo};
-            tc_prim_draw(g, pl, q);
-        }
-    };
-    const bool once = total <= TC_RGBE_MAX_SEGS;
-    if (once && total > 0) setup(0, total);
-    for (int band = 0; band < a.n_bands; band++) {
-        const int y_lo = band * a.rows_per_band;
-        const int y_hi = min(a.H, y_lo + a.rows_per_band);
-        uint8_t *out = a.obs + ((size_t)env * a.H + y_lo) * a.W * 3;
-        const bool drew = once ? (total > 0 && ((band_mask >> (band & 31)) & 1u)) : total > 0;
-        if (drew) {
-            for (int i = tid; i < C * a.plane_words + 1; i += TC_RASTER_THREADS) planes[i] = 0;
-            __syncthreads();
-            if (once) draw(total, y_lo, y_hi);
-            else
-                for (int first = 0; first < total; first += TC_RGBE_MAX_SEGS) {
-                    const int n = min(TC_RGBE_MAX_SEGS, total - first);
-                    setup(first, n);
-                    draw(n, y_lo, y_hi);
-                    __syncthreads();
-                }
-            __syncthreads();
-            for (int i = tid; i <= a.plane_words; i += TC_RASTER_THREADS) {
-                uint32_t v = 0;
-                if (i < a.plane_words)
-                    for (int c = 0; c < C; c++) v |= planes[(size_t)c * a.plane_words + i];
-                any_plane[i] = v;
-            }
-            __syncthreads();
-        }
-        tc_store_rgb<TC_RASTER_THREADS>(out, (uint32_t)((y_hi - y_lo) * a.W), planes, (uint32_t)a.plane_words * 32u, C, color24, drew, any_plane);
-        __syncthreads();   // the next band reuses the planes
-    }
-}
+#define TC_RGBE_MAX_SEGS 48   // segments whose primitive slots a block-per-env banded kernel keeps in shared memory at once
 
 // ------------------------------------------------------------------------------------------------ fused camera pass + rasterise + store
 // classes, single band: a block per (env, class) runs the camera pass in shared memory, keeps the segments on chip,
