@@ -272,3 +272,37 @@ def test_nearest_laneline_index_equals_the_full_scan(map_name):
     assert info[0] > 1000 and (cand >= 0).mean() > 0.7, "the index should cover the map"
     m_total = int(tables.ll_edge_off[-1])
     assert info[1] < 0.25 * m_total / C + 8, ("lists should be short", info)
+
+
+def test_table_builders_survive_degenerate_maps():
+    """Visible-set tables and nearest-laneline index on maps with an empty class, a class of one isolated node, coincident
+    nodes and a self-loop edge: the builders must not crash and the culled camera pass / indexed search must still equal the
+    plain ones."""
+    data = {"height": 300, "width": 300,
+            "lanelines": {"empty": {"layer_color": [1, 2, 3], "nodes": [], "edges": []},
+                          "dot": {"layer_color": [9, 9, 9], "nodes": [[50, 50]], "edges": []},
+                          "twin": {"layer_color": [255, 0, 0], "nodes": [[100, 100], [100, 100], [140, 100], [140, 160]], "edges": [[0, 1], [1, 2], [2, 3], [3, 3]]},
+                          "line": {"layer_color": [0, 255, 0], "nodes": [[10 + 20 * i, 200] for i in range(12)], "edges": [[i, i + 1] for i in range(11)]}},
+            "lanepath": {"layer_color": [0, 0, 0], "nodes": [[20, 150], [120, 150], [220, 150]], "edges": [[0, 1], [1, 2]]}}
+    tables = MapTables(data, 100)
+    cc = {"position": [0, -0.005, 0.04], "orientation": [22, 0, 0], "fov": 80, "resolution": [96, 128], "max_range": 0.6}
+    row = camera_row(cc["position"], cc["orientation"], cc["fov"], cc["resolution"], cc["max_range"])
+    rng = np.random.default_rng(0)
+    n = 3000
+    xy = rng.uniform(-0.5, 3.5, (n, 2))
+    rot = rng.uniform(-np.pi, np.pi, n)
+    env = HostCore(tables, n, np.zeros(8), row, 2, 96, 128)
+    env.pose[:] = _poses(row[:12].reshape(3, 4), xy, rot)
+    env.obs = None
+    env.render()
+    radius = ht().ht_cull_radius_of(P(row), 96, 128)
+    cnt, seg, cell_nodes, info = env.project_culled(radius, cell=0.2)
+    assert same_segments(tables, cnt, seg, env.seg_count, env.seg)
+    assert env.seg_count.sum() > 0
+    pts = np.ascontiguousarray(rng.uniform(-0.5, 3.5, (4000, 2)))
+    full = np.zeros((len(pts), tables.n_classes), np.int32)
+    got = np.zeros_like(full)
+    ht().ht_nearest(env.h, len(pts), P(pts), 0, 1, P(full), None, None)
+    ht().ht_nearest(env.h, len(pts), P(pts), 1, 32, P(got), None, None)
+    assert np.array_equal(got, full)
+    assert (full[:, 0] == -1).all() and (full[:, 1] == -1).all()   # classes without edges have no nearest edge

@@ -2,9 +2,10 @@
 
 The vectorised counterpart of the reference's TinyCarloEnv (tinycarlo/env.py:15-147): same config schema, same action
 dict ({"car_control": [velocity cmd, steering cmd] in [-1,1], "maneuver": 0..3}), same observation formats and the
-same info keys, batched along dim 0. One step() enqueues three hand-written sm_100a kernels through the C ABI
-(tracking, camera pass, rasterise+store) on torch's current stream and returns views of preallocated tensors; there
-is no host synchronisation inside step() and no CPU implementation.
+same info keys, batched along dim 0. One step() enqueues two hand-written sm_100a kernels through the C ABI (tracking;
+fused camera pass + rasterise + store) on torch's current stream and returns views of preallocated tensors; there is no
+host synchronisation inside step() - resets and spawn draws included, so a rollout loop can be captured in a CUDA graph -
+and no CPU implementation.
 
 Returned tensors are owned by the env and are overwritten by the next step()/reset(); clone what must survive.
 """
