@@ -819,7 +819,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_classes_kernel(const 
 //    TC_SMALL_PRIM_ITEMS items is handed to the whole warp on the spot;
 //  * shared memory is reused aggressively: the segment list overlays the camera-frame coordinates once they are projected,
 //    plane and primitive slots overlay the projected coordinates, flags and tables.
-#define TC_SMALL_PRIM_ITEMS 48
+#ifndef TC_SMALL_PRIM_ITEMS
+#define TC_SMALL_PRIM_ITEMS 24 // measured 12 / 24 / 48 / 96: 24.6 / 24.7 / 23.9 / 23.3 M env-steps/s on Knuffingen 128x160
+#endif
 #define TC_ENV_CHUNK 32
 __device__ __forceinline__ int tc_prim_items(const TcPrim &q) {
     if (q.kind == TC_PRIM_LINE2) return q.a[4] + 1;
