@@ -87,6 +87,7 @@ struct TcHandle {
     size_t envb_smem = 0;    // tc_render_env_banded_kernel (large frames, RGB / 1 bit per pixel); 0: not available
     int envb_rows = 0, envb_bands = 0, envb_words = 0, envb_on = 1;
     double cull_radius = -1.0, cull_mean_nodes = 0.0;
+    bool cull_built_once = false;
     int cull_cells = 0, cull_max_nodes = 0;
     uint8_t *ar_done = nullptr; // autoreset flags: caller-owned device buffer
     uint64_t *rng = nullptr;    // spawn streams: caller-owned device buffers
@@ -382,7 +383,15 @@ int tc_set_camera_params(TcHandle *h, const double *dev_cam, const int32_t *dev_
             double r = tc_cull_radius_of(rows.data() + (size_t)i * TC_CAM_N, h->H, h->W);
             radius = r < 0 ? -1.0 : std::max(radius, r);
         }
-        if (radius != h->cull_radius && !(radius >= 0 && h->cull_radius >= radius && h->cull_radius <= 1.05 * radius)) TC_TRY(tc_install_cull(h, radius));
+        // Tables built for a larger reach stay exact for a smaller one (only less tight): rebuild when the cameras see farther
+        // than the tables allow, or less than half as far. The first tables are tight; when the reach keeps changing (camera
+        // randomisation per episode through the single-env drop-in) later ones get 25 % headroom so that rebuilds die out.
+        const bool keep = radius >= 0 && h->cull_radius >= radius && h->cull_radius <= 2.0 * radius;
+        if (radius != h->cull_radius && !keep) {
+            const bool first = !h->cull_built_once;
+            TC_TRY(tc_install_cull(h, radius < 0 || first ? radius : 1.25 * radius));
+            h->cull_built_once = true;
+        }
     }
     return TC_OK;
 }
