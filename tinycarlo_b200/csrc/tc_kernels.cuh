@@ -864,6 +864,66 @@ __host__ __device__ inline size_t tc_env_smem_bytes(size_t np, int max_bytes, in
     return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
+// The camera pass of the block-per-env kernels (camera.py:52-110) on the sub-graph of the camera's ground cell: transform,
+// the four ordered clip passes, projection, visibility (core nodes only), kept edges. In: the cell's tables at tab_smem
+// (landing via TMA, mbarrier `bar`), pose and intrinsics in shared memory. Out: *seg_cnt segments as int4 at smem_raw, their
+// classes as bytes behind them (segs + d.n_edges); the scratch arrays it used are dead afterwards. All threads call it.
+template <int NT>
+__device__ __forceinline__ void tc_env_camera_pass(unsigned char *smem_raw, size_t np, const unsigned char *tab_smem, const TcCellBlob &d,
+                                               uint64_t *bar, const double *pose, const double *cam, int H, int W, int *seg_cnt) {
+    const int tid = threadIdx.x;
+    const int n = d.n_nodes, m = d.n_edges;
+    int4 *segs = (int4 *)smem_raw;
+    TcProjScratch sc;
+    sc.Px = (double *)smem_raw; sc.Py = sc.Px + np; sc.Pz = sc.Py + np;
+    sc.ix = (int32_t *)(sc.Pz + np); sc.iy = sc.ix + np;
+    uint8_t *fA = (uint8_t *)(sc.iy + np), *fB = fA + np, *rA = fB + np, *rB = rA + np;
+    sc.vis = rB + np; sc.front = fA; sc.inr = rA;
+    const double max_range = cam[TC_CAM_MAX_RANGE];
+    tc_mbar_wait(bar, 0); // the cell's tables have landed in shared memory
+    const TcClassTables ct = tc_class_tables_from_cell(tab_smem, d);
+    const uint8_t *core = tab_smem + d.off_core, *edge_cls = tab_smem + d.off_edge_cls;
+    for (int v = tid; v < n; v += NT) {
+        double X, Y, Z;
+        tc_transform_node(pose, ct.nodes[2 * v], ct.nodes[2 * v + 1], X, Y, Z);
+        sc.Px[v] = X; sc.Py[v] = Y; sc.Pz[v] = Z;
+        fA[v] = Z < 0;
+    }
+    __syncthreads();
+    // camera.py:70-77 near-plane fix-ups, :80-86 range fix-ups (depths is a live view: evaluated on the moved z): the four
+    // ordered passes in ONE loop (one instance of the pass in the code; the flags ping-pong between two arrays)
+    for (int pass = 0; pass < 4; pass++) {
+        const bool range = pass >= 2, outgoing = (pass & 1) == 0;
+        const double tz = range ? -max_range : -0.0000001;
+        uint8_t *src = range ? (outgoing ? rA : rB) : (outgoing ? fA : fB), *dst = range ? (outgoing ? rB : rA) : (outgoing ? fB : fA);
+        if (pass == 2) {
+            for (int v = tid; v < n; v += NT) rA[v] = sc.Pz[v] > -max_range;
+            __syncthreads();
+        }
+        for (int v = tid; v < n; v += NT) dst[v] = src[v] | (uint8_t)tc_clip_pass_node(ct, sc, src, v, outgoing, tz);
+        __syncthreads();
+    }
+    for (int v = tid; v < n; v += NT) {
+        double u, w;
+        tc_project(cam, sc.Px[v], sc.Py[v], sc.Pz[v], u, w);
+        sc.ix[v] = tc_np_int32(u);
+        sc.iy[v] = tc_np_int32(w);
+        sc.vis[v] = (core[v] && u > 0 && u < W && w > 0 && w < H && fA[v] && rA[v]) ? 1 : 0;
+    }
+    __syncthreads();   // the camera-frame coordinates are dead: the segment list takes their place
+    uint8_t *seg_cls = (uint8_t *)(segs + m);
+    // kept edges (camera.py:95); order is irrelevant for single-colour planes, and in RGB the classes keep their order
+    for (int e = tid; e < m; e += NT) {
+        int n0 = ct.edges[2 * e], n1 = ct.edges[2 * e + 1];
+        if (sc.vis[n0] || sc.vis[n1]) {
+            int slot = atomicAdd(seg_cnt, 1);
+            segs[slot] = make_int4(sc.ix[n0], sc.iy[n0], sc.ix[n1], sc.iy[n1]);
+            seg_cls[slot] = edge_cls[e];
+        }
+    }
+    __syncthreads();   // projected coordinates, flags and tables are dead: plane and primitive slots take their place
+}
+
 template <int NT, int FMT>
 __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRenderEnvArgs a) {
     constexpr bool RGB = FMT == TC_FMT_RGB;
@@ -909,56 +969,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRe
     uint32_t *plane = (uint32_t *)(smem_raw + tc_env_off_plane(np));
     int32_t *pw = (int32_t *)(smem_raw + tc_env_off_prims(np, a.plane_words));
     if (n > 0) {
-        TcProjScratch sc;
-        sc.Px = (double *)smem_raw; sc.Py = sc.Px + np; sc.Pz = sc.Py + np;
-        sc.ix = (int32_t *)(sc.Pz + np); sc.iy = sc.ix + np;
-        uint8_t *fA = (uint8_t *)(sc.iy + np), *fB = fA + np, *rA = fB + np, *rB = rA + np;
-        sc.vis = rB + np; sc.front = fA; sc.inr = rA;
-        const double *pose = s_pose, *cam = s_cam;
-        const double max_range = cam[TC_CAM_MAX_RANGE];
-        tc_mbar_wait(&bar, 0); // the cell's tables have landed in shared memory
-        TC_TL(tl1 = clock64());
-        const TcClassTables ct = tc_class_tables_from_cell(tab_smem, s_desc);
-        const uint8_t *core = tab_smem + s_desc.off_core, *edge_cls = tab_smem + s_desc.off_edge_cls;
-        for (int v = tid; v < n; v += NT) {
-            double X, Y, Z;
-            tc_transform_node(pose, ct.nodes[2 * v], ct.nodes[2 * v + 1], X, Y, Z);
-            sc.Px[v] = X; sc.Py[v] = Y; sc.Pz[v] = Z;
-            fA[v] = Z < 0;
-        }
-        __syncthreads();
-        // camera.py:70-77 near-plane fix-ups, :80-86 range fix-ups (depths is a live view: evaluated on the moved z): the four
-        // ordered passes in ONE loop (one instance of the pass in the code; the flags ping-pong between two arrays)
-        for (int pass = 0; pass < 4; pass++) {
-            const bool range = pass >= 2, outgoing = (pass & 1) == 0;
-            const double tz = range ? -max_range : -0.0000001;
-            uint8_t *src = range ? (outgoing ? rA : rB) : (outgoing ? fA : fB), *dst = range ? (outgoing ? rB : rA) : (outgoing ? fB : fA);
-            if (pass == 2) {
-                for (int v = tid; v < n; v += NT) rA[v] = sc.Pz[v] > -max_range;
-                __syncthreads();
-            }
-            for (int v = tid; v < n; v += NT) dst[v] = src[v] | (uint8_t)tc_clip_pass_node(ct, sc, src, v, outgoing, tz);
-            __syncthreads();
-        }
-        for (int v = tid; v < n; v += NT) {
-            double u, w;
-            tc_project(cam, sc.Px[v], sc.Py[v], sc.Pz[v], u, w);
-            sc.ix[v] = tc_np_int32(u);
-            sc.iy[v] = tc_np_int32(w);
-            sc.vis[v] = (core[v] && u > 0 && u < a.W && w > 0 && w < a.H && fA[v] && rA[v]) ? 1 : 0;
-        }
-        __syncthreads();   // the camera-frame coordinates are dead: the segment list takes their place
-        uint8_t *seg_cls = (uint8_t *)(segs + m);
-        // kept edges (camera.py:95); order is irrelevant for single-colour planes, and in RGB the classes keep their order
-        for (int e = tid; e < m; e += NT) {
-            int n0 = ct.edges[2 * e], n1 = ct.edges[2 * e + 1];
-            if (sc.vis[n0] || sc.vis[n1]) {
-                int slot = atomicAdd(&seg_cnt, 1);
-                segs[slot] = make_int4(sc.ix[n0], sc.iy[n0], sc.ix[n1], sc.iy[n1]);
-                seg_cls[slot] = edge_cls[e];
-            }
-        }
-        __syncthreads();   // projected coordinates, flags and tables are dead: plane and primitive slots take their place
+        tc_env_camera_pass<NT>(smem_raw, np, tab_smem, s_desc, &bar, s_pose, s_cam, a.H, a.W, &seg_cnt);
     }
     const int cnt = seg_cnt;
     TC_TL(tl2 = clock64());
@@ -1091,55 +1102,7 @@ __global__ void __launch_bounds__(256, 4) tc_render_env_banded_kernel(const TcRe
     uint32_t *planes = (uint32_t *)(smem_raw + np * 24);
     uint32_t *any_plane = (uint32_t *)(smem_raw + tc_envb_off_any(np, C, a.band_words));
     int32_t *pw = (int32_t *)(smem_raw + tc_envb_off_prims(np, C, a.band_words));
-    if (n > 0) {
-        // ---- camera pass (camera.py:52-110) on the cell's sub-graph, exactly as in tc_render_env_kernel
-        TcProjScratch sc;
-        sc.Px = (double *)smem_raw; sc.Py = sc.Px + np; sc.Pz = sc.Py + np;
-        sc.ix = (int32_t *)(sc.Pz + np); sc.iy = sc.ix + np;
-        uint8_t *fA = (uint8_t *)(sc.iy + np), *fB = fA + np, *rA = fB + np, *rB = rA + np;
-        sc.vis = rB + np; sc.front = fA; sc.inr = rA;
-        const double *pose = s_pose, *cam = s_cam;
-        const double max_range = cam[TC_CAM_MAX_RANGE];
-        tc_mbar_wait(&bar, 0);
-        const TcClassTables ct = tc_class_tables_from_cell(tab_smem, s_desc);
-        const uint8_t *core = tab_smem + s_desc.off_core, *edge_cls = tab_smem + s_desc.off_edge_cls;
-        for (int v = tid; v < n; v += NT) {
-            double X, Y, Z;
-            tc_transform_node(pose, ct.nodes[2 * v], ct.nodes[2 * v + 1], X, Y, Z);
-            sc.Px[v] = X; sc.Py[v] = Y; sc.Pz[v] = Z;
-            fA[v] = Z < 0;
-        }
-        __syncthreads();
-        for (int pass = 0; pass < 4; pass++) {
-            const bool range = pass >= 2, outgoing = (pass & 1) == 0;
-            const double tz = range ? -max_range : -0.0000001;
-            uint8_t *src = range ? (outgoing ? rA : rB) : (outgoing ? fA : fB), *dst = range ? (outgoing ? rB : rA) : (outgoing ? fB : fA);
-            if (pass == 2) {
-                for (int v = tid; v < n; v += NT) rA[v] = sc.Pz[v] > -max_range;
-                __syncthreads();
-            }
-            for (int v = tid; v < n; v += NT) dst[v] = src[v] | (uint8_t)tc_clip_pass_node(ct, sc, src, v, outgoing, tz);
-            __syncthreads();
-        }
-        for (int v = tid; v < n; v += NT) {
-            double u, w;
-            tc_project(cam, sc.Px[v], sc.Py[v], sc.Pz[v], u, w);
-            sc.ix[v] = tc_np_int32(u);
-            sc.iy[v] = tc_np_int32(w);
-            sc.vis[v] = (core[v] && u > 0 && u < a.W && w > 0 && w < a.H && fA[v] && rA[v]) ? 1 : 0;
-        }
-        __syncthreads();
-        uint8_t *seg_cls_w = (uint8_t *)(segs + m);
-        for (int e = tid; e < m; e += NT) {
-            int n0 = ct.edges[2 * e], n1 = ct.edges[2 * e + 1];
-            if (sc.vis[n0] || sc.vis[n1]) {
-                int slot = atomicAdd(&seg_cnt, 1);
-                segs[slot] = make_int4(sc.ix[n0], sc.iy[n0], sc.ix[n1], sc.iy[n1]);
-                seg_cls_w[slot] = edge_cls[e];
-            }
-        }
-        __syncthreads();
-    }
+    if (n > 0) tc_env_camera_pass<NT>(smem_raw, np, tab_smem, s_desc, &bar, s_pose, s_cam, a.H, a.W, &seg_cnt);
     const int total = seg_cnt;
     const uint8_t *seg_cls = (const uint8_t *)(segs + m);
     const int t = a.thickness[env];
