@@ -976,8 +976,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRe
     const int n_planes = a.n_classes;
     if (cnt > 0) {
         const uint8_t *seg_cls = (const uint8_t *)(segs + m);
-        for (int i = tid; i < a.plane_words; i += NT) plane[i] = 0;
-        __syncthreads();
+        // the plane is zeroed by the warps that have no role in the first set-up round (when the block has more warps than roles)
+        constexpr bool ZERO_IN_SETUP = NT / 32 > TC_N_ROLES;
+        if (!ZERO_IN_SETUP) {
+            for (int i = tid; i < a.plane_words; i += NT) plane[i] = 0;
+            __syncthreads();
+        }
         TC_TL(tl_z = clock64());
         const int t = a.thickness[env];
         const int warp = tid >> 5, lane = tid & 31;
@@ -988,7 +992,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRe
             for (int i = tid; i < nseg * TC_MAX_PRIMS_PER_SEG; i += NT)
                 pw[(i / TC_MAX_PRIMS_PER_SEG) * TC_ENV_SEG_WORDS + (i % TC_MAX_PRIMS_PER_SEG) * 8] = TC_PRIM_NONE;
             __syncthreads();
-            if (lane < nseg) {
+            if (ZERO_IN_SETUP && base == 0 && warp >= TC_N_ROLES) {
+                for (int i = tid - TC_N_ROLES * 32; i < a.plane_words; i += NT - TC_N_ROLES * 32) plane[i] = 0;
+            } else if (lane < nseg) {
                 int4 s4 = segs[base + lane];
                 for (int role = warp; role < TC_N_ROLES; role += NT / 32)
                     tc_polyline_setup<true>(a.W, a.H, s4.x, s4.y, s4.z, s4.w, t, role, (TcPrim *)(pw + lane * TC_ENV_SEG_WORDS));
