@@ -9,12 +9,17 @@
  *   tc_set_camera_params   Camera.__init__/update_params (tinycarlo/camera.py:12-27,48-50): E (3x4), K, max_range,
  *                          line_thickness per env; E and K are built on the host (camera.py:145-178)
  *   tc_reset               TinyCarloEnv.reset -> Car.reset -> Map.sample_spawn (env.py:101-113, car.py:34-44,
- *                          map.py:51-69) for the masked envs, spawn nodes drawn by the caller
+ *                          map.py:51-69) for the masked envs; spawn nodes given by the caller or drawn on the device
+ *   tc_set_spawn_rng       the env's np_random (gymnasium seeding of Env.reset(seed), used by map.py:61): one
+ *                          numpy-compatible PCG64 stream per env, advanced by the reset paths on the device
+ *   tc_set_autoreset       no counterpart (the reference leaves resets to the caller): gymnasium's next-step autoreset
+ *                          inside tc_step
  *   tc_step                TinyCarloEnv.step (env.py:115-147): Car.step + find_local_path (car.py:70-148),
  *                          Camera.capture_frame (camera.py:52-110), Renderer.render_camera_frame_classes/_rgb
  *                          (renderer.py:36-51), Car.get_info (car.py:46-68), default reward/termination (env.py:87-99)
  *   tc_render              Camera.capture_frame alone at the current poses (used after tc_reset / tc_set_state)
  *   tc_get_state/set_state direct access to Car.position/rotation/steering_angle/velocity/local_path/last_maneuver
+ *   tc_noise_blobs         NoiseObservationWrapper.observation (tinycarlo/wrapper/observation.py:14-27) with a counter-based RNG
  *   tc_step_host           the same step driven with HOST buffers (pinned or pageable): actions are copied in and the
  *                          scalar results copied out inside the call; used for the end-to-end measurement
  *
