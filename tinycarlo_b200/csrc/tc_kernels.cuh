@@ -1,13 +1,19 @@
 // tc_kernels.cuh — sm_100a kernels of the hot path. Included by tc_api.cu only.
 //
-//   tc_track_kernel     a warp per env: bicycle step, local-path selection, CTE / heading / laneline distances,
-//                       reward, pose for the camera. Map tables are staged once per block into shared memory with a
-//                       1-D TMA bulk copy (cp.async.bulk + mbarrier) and shared by the block's 8 envs.
-//   tc_project_kernel   a block per (env, class): transform the class's nodes, the four ordered clip passes in
-//                       node-parallel form, projection, endpoint culling, ordered compaction of the kept segments.
-//   tc_raster_kernel    a block per (env, plane band): OpenCV-exact rasterisation of the kept segments into a 1-bit
-//                       plane in shared memory, then bits -> bytes with 128-bit streaming stores; every output byte is
-//                       written exactly once. Classes: one plane per block. RGB: C planes + painter's-order compose.
+//   tc_track_kernel              a warp per env: bicycle step, local-path selection, CTE / heading / laneline distances
+//                                (nearest-laneline index), reward, flags, pose for the camera, resets with device-side spawn
+//                                draws. Map tables are staged once per block into shared memory with a 1-D TMA bulk copy
+//                                (cp.async.bulk + mbarrier) and shared by the block's 8 envs.
+//   tc_render_classes_kernel     THE HEADLINE KERNEL (large u8 / bf16 / bit frames): a block per (env, class) - camera pass,
+//                                polyline set-up, drawing into a 1-bit plane in shared memory, bits -> bytes with 128-bit
+//                                streaming stores; every output byte is written exactly once. Runs at the HBM write ceiling.
+//   tc_render_env_kernel         small frames: a block per env renders all classes, camera pass on the visible-set
+//                                sub-graph of the camera's ground cell, one thread per primitive.
+//   tc_render_env_banded_kernel  large RGB / bit-packed frames: a block per env, set-up once, row bands inside the block.
+//   tc_project_kernel + tc_raster_classes_kernel / tc_raster_rgb_kernel
+//                                the unfused fallback (segments through global memory, a block per row band) and the
+//                                debug segment export.
+//   tc_noise_blobs_kernel        NoiseObservationWrapper; tc_debug_layer_kernel: layer.py known-answer hook for the tests.
 #pragma once
 #include <cuda_runtime.h>
 
