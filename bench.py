@@ -261,6 +261,33 @@ def main():
         w1.record()
         torch.cuda.synchronize(dev)
         write_ceiling = max(write_ceiling, env.obs.numel() / (w0.elapsed_time(w1) * 1e-3) / 1e9)
+    # ... and the driver's own memset of the same tensor (cudaMemsetAsync through libcudart): the pure-write ceiling of this box
+    memset_gbs = None
+    if not args.no_fill_context:
+        try:
+            import ctypes
+            rt = None
+            for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+                try:
+                    rt = ctypes.CDLL(name)
+                    break
+                except OSError:
+                    continue
+            if rt is not None:
+                rt.cudaMemsetAsync.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+                nbytes = env.obs.numel() * env.obs.element_size()
+                stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                best = 0.0
+                for _ in range(3):
+                    w0.record()
+                    rc = rt.cudaMemsetAsync(ctypes.c_void_p(env.obs.data_ptr()), 0, nbytes, stream)
+                    w1.record()
+                    torch.cuda.synchronize(dev)
+                    if rc == 0:
+                        best = max(best, nbytes / (w0.elapsed_time(w1) * 1e-3) / 1e9)
+                memset_gbs = best or None
+        except Exception:
+            memset_gbs = None
     # ---- the same host loop WITH the observations copied to pinned host memory every step (what the single-env gymnasium
     # drop-in does), on a reduced batch so that it stays a measurement of the path and not of minutes of PCIe: rank 0 only
     e2e_obs = None
@@ -320,7 +347,7 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "step_share_ms": {k: v / max(kern_steps, 1) for k, v in kern_ms.items()},
                 "frac_of_nominal_8tbs": achieved / 8000.0,
-                "torch_zero_fill_gbs": write_ceiling if write_ceiling > 0 else None}
+                "torch_zero_fill_gbs": write_ceiling if write_ceiling > 0 else None, "cuda_memset_gbs": memset_gbs}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
