@@ -192,6 +192,9 @@ def _poses(E, xy, rot):
     ("knuffingen", 222, [128, 160], {}), ("knuffingen", 222, [480, 640], {"max_range": 1.5}), ("knuffingen", 222, [84, 84], {"fov": 125, "orientation": [10, 0, 0]}),
     ("knuffingen", 222, [128, 160], {"max_range": 0.2, "position": [0.02, -0.01, 0.02], "orientation": [35, 4, -6]}),
     ("simple_layout", 450, [84, 84], {}), ("simple_layout", 450, [84, 84], {"max_range": 0.15}),
+    ("knuffingen", 222, [96, 128], {"orientation": [1, 0, 0], "max_range": 1.0}),                       # looking almost horizontally
+    ("knuffingen", 222, [96, 128], {"orientation": [88, 0, 0], "position": [0, 0, 0.3], "fov": 150}),   # looking almost straight down, very wide
+    ("simple_layout", 450, [64, 64], {"orientation": [22, 30, 90], "position": [0.05, 0.03, 0.01]}),    # rolled, yawed, 1 cm above the ground
     ("formula_student_track", 100, [128, 160], {"max_range": 3.0}), ("formula_student_skidpad", 100, [96, 128], {"max_range": 1.0})])
 def test_visible_set_tables_never_change_the_segments(map_name, ppm, res, cam):
     """tc_cull.h: the camera pass on the sub-graph of the camera's ground cell emits exactly the segments of the pass over the
