@@ -558,3 +558,24 @@ def test_cuda_banded_env_kernel_with_many_segments(thickness):
     assert most > 48, most
     for e in (env_rgb, env_bits, env_seg):
         e.close()
+
+
+@pytest.mark.parametrize("fmt,res", [("classes", [45, 71]), ("rgb", [45, 71]), ("classes", [33, 35]), ("rgb", [481, 643]), ("classes", [481, 643])])
+def test_cuda_odd_resolutions_match_oracle(fmt, res):
+    """Frames whose rows and per-env strides are not multiples of 16 bytes (unaligned heads / tails of the vector stores, partial
+    plane words), small and large, through every render path."""
+    n = 24 if res[0] > 400 else 192
+    cfg = make_config("knuffingen", fmt, cam={"resolution": res})
+    env, oenv = _vec(cfg, n), oracle_env(cfg, n)
+    rng = np.random.default_rng(res[0])
+    env.reset(seed=2)
+    oenv.reset(env._spawn_nodes.cpu().numpy())
+    assert np.array_equal(env.obs.cpu().numpy(), oenv.obs)
+    for t in range(6):
+        cc = np.stack([rng.uniform(0.3, 1, n), rng.uniform(-1, 1, n)], 1).astype(np.float32)
+        man = rng.integers(0, 4, n).astype(np.int32)
+        env.step({"car_control": torch.from_numpy(cc).cuda(), "maneuver": torch.from_numpy(man).cuda()})
+        oenv.step(cc.astype(np.float64), man)
+        assert np.array_equal(env.obs.cpu().numpy(), oenv.obs), (fmt, res, t)
+    assert oenv.obs.any()
+    env.close()
