@@ -113,6 +113,9 @@ typedef struct {
 
 TC_API int tc_abi_version(void);
 TC_API const char *tc_last_error(void);
+/* 16 hex digits: hash of the sources and compiler flags this library was built from (the loader compares it with the
+ * sources next to it, so a stale prebuilt library is never used silently; benchmarks print it with their numbers). */
+TC_API const char *tc_build_info(void);
 
 TC_API int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int32_t device, TcHandle **out);
 TC_API int tc_destroy(TcHandle *h);
@@ -138,6 +141,10 @@ TC_API int tc_set_spawn_rng(TcHandle *h, uint64_t *dev_rng_state, const int32_t 
  * dev_done[i] = terminated | truncated. dev_done is caller-owned device memory that must stay alive; the caller may OR
  * further termination conditions (wrappers) into it between steps. NULL = off. */
 TC_API int tc_set_autoreset(TcHandle *h, uint8_t *dev_done /*[N]*/);
+/* Optional companion of tc_set_autoreset: every tc_step writes dev_was_reset[i] = 1 for the envs it reset instead of
+ * advancing (what gymnasium's vector env reports as the autoreset step), 0 otherwise. The vectorised reward /
+ * termination wrappers (tinycarlo/wrapper/reward.py, termination.py) use it to leave reset steps alone. NULL = off. */
+TC_API int tc_set_reset_mask(TcHandle *h, uint8_t *dev_was_reset /*[N]*/);
 
 /* Reset the envs with dev_mask[i] != 0 (NULL = all) to lanepath node dev_spawn_nodes[i], or - dev_spawn_nodes NULL - to a
  * node drawn from the env's device stream; renders into obs if non-NULL and zeroes their info outputs like the
@@ -156,6 +163,13 @@ TC_API int tc_set_state(TcHandle *h, const double *dev_sf, const int32_t *dev_si
 TC_API int tc_step_host(TcHandle *h, const float *host_car_control, const int32_t *host_maneuver, const TcOutputs *dev_outs,
                  float *host_reward, uint8_t *host_terminated, uint8_t *host_truncated, float *host_cte, float *host_heading_error,
                  void *stream);
+/* The same, and the step's observations (dev_outs->obs, obs_bytes bytes: all envs) are copied to host_obs with ONE
+ * device-to-host copy before the synchronisation - what the reference's caller holds after env.step (env.py:147 returns the
+ * frame as a host array). With the 1-bit-per-pixel format (TC_OBS_CLASSES_BITS) that is 8x fewer PCIe bytes than u8 masks. */
+#include <stddef.h>
+TC_API int tc_step_host_obs(TcHandle *h, const float *host_car_control, const int32_t *host_maneuver, const TcOutputs *dev_outs,
+                 float *host_reward, uint8_t *host_terminated, uint8_t *host_truncated, float *host_cte, float *host_heading_error,
+                 void *host_obs, size_t obs_bytes, void *stream);
 
 /* NoiseObservationWrapper (tinycarlo/wrapper/observation.py:5-33) on u8 class observations [N,C,H,W], in place: per class
  * n_blobs filled circles (centre uniform in the frame, radius uniform in [1, max_radius)), each with probability 0.3 ORs in

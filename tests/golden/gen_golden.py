@@ -100,7 +100,10 @@ class Recorder:
 
 
 def run_scenario(name, cfg, n_steps, policy, seed, wrappers=(), reset_mode="continue", rgb_keep_every=25,
-                 cam_mutations=None):
+                 cam_mutations=None, action_dtype="pyfloat"):
+    """action_dtype: "pyfloat" feeds car_control as a list of Python floats (the float64 path every bit-exact test uses);
+    "float32" feeds np.float32 ndarrays - what action_space.sample() yields - which makes numpy >= 2 keep parts of the
+    reference's state in float32: recorded for the tolerance test of that case only."""
     rec = Recorder()
     try:
         env = gym.make("tinycarlo-v2", config=ref_config(cfg))
@@ -180,7 +183,8 @@ def run_scenario(name, cfg, n_steps, policy, seed, wrappers=(), reset_mode="cont
             cc = [f32(cc[0]), f32(cc[1])]
             act_cc.append(cc)
             act_man.append(int(man))
-            obs, reward, terminated, truncated, info = env.step({"car_control": cc, "maneuver": int(man)})
+            fed = np.array(cc, dtype=np.float32) if action_dtype == "float32" else cc
+            obs, reward, terminated, truncated, info = env.step({"car_control": fed, "maneuver": int(man)})
             record(1, t, None, obs, info, reward, terminated, truncated)
             if terminated or truncated:
                 if reset_mode == "continue":
@@ -202,7 +206,7 @@ def run_scenario(name, cfg, n_steps, policy, seed, wrappers=(), reset_mode="cont
         out["act_man"] = np.array(act_man, dtype=np.int32)
         meta = {"name": name, "config": cfg, "wrappers": list(wrappers), "seed": seed, "reset_mode": reset_mode,
                 "class_names": base.map.get_laneline_names(), "numpy": np.__version__, "cv2": cv2.__version__,
-                "n_steps": n_steps,
+                "n_steps": n_steps, "action_dtype": action_dtype,
                 "cam_mutations": {str(k): v for k, v in (cam_mutations or {}).items()}}
         out["meta"] = np.array(json.dumps(meta))
         path = os.path.join(HERE, name + ".npz")
@@ -318,6 +322,11 @@ def main():
                                                                                 "area": 0.25}}),
                                ("LanelineCrossingTerminationWrapper", {"lanelines": ["outer", "solid"]})],
                      reset_mode="reseed", rgb_keep_every=1000)
+    # J. float32 ndarray actions (action_space.sample() dtype): the reference then computes parts of the car state in float32
+    if want("knuff_f32_actions"):
+        run_scenario("knuff_f32_actions", make_config("knuffingen", "classes", cam={"resolution": [64, 96]}), 200,
+                     make_stanley(0.8, 4.0, 0, noise_sigma=0.3, switch_every=50), seed=13, rgb_keep_every=1000,
+                     action_dtype="float32")
     # I. spawn RNG parity: many seeds, draws per seed (map.py:51-69), with and without spawn_points
     if want("spawn_draws"):
         res = {}

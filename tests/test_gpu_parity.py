@@ -53,11 +53,14 @@ def cam_row_from(E, K, mr):
     return r
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["unfused+segments", "fused"])
 @pytest.mark.parametrize("name", SCENARIOS)
-def test_cuda_replays_reference_trace(name):
-    """One env driven with the recorded actions must reproduce the reference's trace."""
+def test_cuda_replays_reference_trace(name, fused):
+    """One env driven with the recorded actions must reproduce the reference's trace - through the unfused kernels, which
+    also export the projected segments (tc_project_kernel + tc_raster_*), and through the fused render kernels that every
+    production step uses (tc_render_classes_kernel / tc_render_env_kernel / tc_render_env_banded_kernel)."""
     g = Golden(name)
-    env = _vec(g.cfg, 1, debug_segments=True)
+    env = _vec(g.cfg, 1, debug_segments=not fused)
     if g.wrapped:
         env.set_wrapped(True)
     mr = g.max_range_per_frame()
@@ -103,6 +106,8 @@ def test_cuda_replays_reference_trace(name):
                 assert hashlib.sha256(rgb.tobytes()).hexdigest().encode() == g["rgb_sha"][f], (name, f)
         else:
             assert hashlib.sha256(o.tobytes()).hexdigest().encode() == g["rgb_sha"][f], (name, f)
+        if fused:
+            continue
         gi, _ = g.segments(f)
         cnt = env.out["seg_count"][0].cpu().numpy()
         seg = env.out["seg_i32"][0].cpu().numpy()
@@ -424,24 +429,30 @@ def test_cuda_policy_formats_equal_the_u8_masks(res, n):
     """obs formats beyond the reference: "classes_bits" and "classes_bf16" carry exactly the u8 class masks."""
     cfg = make_config("knuffingen", "classes", cam={"resolution": res})
     envs = {f: _vec(cfg, n, obs_format=f) for f in ("classes", "classes_bf16")}
+    oenv = oracle_env(cfg, n)
     if (res[0] * res[1]) % 32 == 0:
         envs["classes_bits"] = _vec(cfg, n, obs_format="classes_bits")
     rng = np.random.default_rng(8)
     for e in envs.values():
         e.reset(seed=4)
+    oenv.reset(envs["classes"]._spawn_nodes.cpu().numpy())
     H, W = res
     for t in range(6):
         cc = torch.from_numpy(np.stack([rng.uniform(0.3, 1, n), rng.uniform(-1, 1, n)], 1).astype(np.float32)).cuda()
         man = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)).cuda()
         for e in envs.values():
             e.step({"car_control": cc, "maneuver": man})
+        oenv.step(cc.cpu().numpy().astype(np.float64), man.cpu().numpy())
         ref = envs["classes"].obs
-        assert int((ref > 0).sum()) > 0
-        assert torch.equal((envs["classes_bf16"].obs.float() * 255).to(torch.uint8), ref)
+        assert int((ref > 0).sum()) > 0 and np.array_equal(ref.cpu().numpy(), oenv.obs)
+        # every format against the ORACLE's masks (not against this library's own u8 output)
+        bf = envs["classes_bf16"].obs
+        assert bf.dtype == torch.bfloat16
+        assert np.array_equal(bf.float().cpu().numpy(), (oenv.obs > 0).astype(np.float32)), "bf16 must be exactly 0.0 / 1.0 where the oracle's mask is 0 / 255"
         if "classes_bits" in envs:
             words = envs["classes_bits"].obs.cpu().numpy().view(np.uint32)           # [n, C, H*W/32]
             bits = np.unpackbits(words.view(np.uint8), axis=-1, bitorder="little")[..., : H * W].reshape(n, -1, H, W)
-            assert np.array_equal(bits * 255, ref.cpu().numpy())
+            assert np.array_equal(bits * 255, oenv.obs)
     for e in envs.values():
         e.close()
 

@@ -109,13 +109,3 @@ def test_drop_in_surface():
     with pytest.raises(KeyError):
         TinyCarloEnv(config={"sim": {}, "car": {}, "camera": {}})
     env.close()
-
-
-def test_gym_make_registration():
-    gym = pytest.importorskip("gymnasium")
-    import tinycarlo_b200  # noqa: F401  (registers tinycarlo-v2)
-    from pair_util import make_config
-    env = gym.make("tinycarlo-v2", config=make_config("simple_layout", "rgb", cam={"resolution": [32, 48]}))
-    obs, info = env.reset(seed=0)
-    assert obs.shape == (32, 48, 3)
-    env.close()

@@ -174,14 +174,17 @@ def test_headline_kernel_keeps_its_register_budget():
     assert m and int(m.group(1)) <= 64, "block-per-env kernel missing or over its register budget"
 
 
-def test_bench_reference_arm_prints_the_contract_line():
-    """bench.py --impl reference (the CPU arm: oracle port on the host cores) prints ONE JSON line with the keys the driver reads."""
+@pytest.mark.parametrize("config", [3, 1, 4, 5])
+def test_bench_reference_arm_prints_the_contract_line(config):
+    """bench.py --impl reference (the CPU arm: the unmodified reference from baseline/_ref, one process per host core, plus
+    the oracle port as a second figure; the port alone when baseline/_ref is absent) prints ONE JSON line with the keys the
+    driver reads, and the same `config` object as this repo's arm would."""
     import json
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-envs", "24"],
-                       capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", str(config), "--steps", "2", "--warmup", "1",
+                        "--cpu-envs", "24", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -190,6 +193,48 @@ def test_bench_reference_arm_prints_the_contract_line():
               "config", "impl", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["value"] > 0 and d["steps"] == 2 and "workload" in d["config"]
-    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
+    assert d["value"] > 0 and d["steps"] == 2 and "workload" in d["config"] and d["config"]["baseline_config"] == config
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    have_ref = os.path.isdir(os.path.join(root, "baseline", "_ref", "tinycarlo"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    if have_ref:
+        assert d["cpu_baseline"]["single_process"]["value"] > 0 and d["cpu_baseline_port"]["kind"] == "port" and d["cpu_baseline_port"]["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    if config == 3:
+        assert d["metric"] == "env-steps/sec (480x640 class obs, Knuffingen)"     # BASELINE.json's metric, unchanged
+        sys.path.insert(0, os.path.join(root, "baseline"))
+        sys.path.insert(0, root)
+        import bench
+        import workloads as WL
+
+        class A:
+            config, envs_per_gpu = 3, 0
+        assert d["config"] == bench.config_dict(WL.WORKLOADS[3], A, 1)      # what the CUDA arm prints: the driver's same_config check
+
+
+def test_shard_groups_partition_every_group():
+    from tinycarlo_b200.distributed import shard_groups
+    sizes = [10922, 10922, 10924]
+    for world in (1, 2, 4, 8, 3):
+        seen = [np.zeros(n, int) for n in sizes]
+        base = np.cumsum([0] + sizes)
+        for r in range(world):
+            local, offs = shard_groups(sizes, r, world)
+            for g, (n, o) in enumerate(zip(local, offs)):
+                seen[g][o - base[g]:o - base[g] + n] += 1
+        assert all((s == 1).all() for s in seen), world
+
+
+def test_gymnasium_registration_with_a_gymnasium_on_the_path():
+    """import tinycarlo_b200 registers tinycarlo-v2 when a gymnasium is importable (tinycarlo/__init__.py:3); checked in a fresh
+    interpreter with the stand-in of tests/golden/gym_stub (gymnasium itself is not in the image). No GPU needed."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import gymnasium as gym, tinycarlo_b200\n"
+            "from tinycarlo_b200 import gym_compat\n"
+            "assert gym_compat.HAVE_GYMNASIUM and gym_compat.Env is gym.Env\n"
+            "assert gym.envs.registration.registry['tinycarlo-v2'] == 'tinycarlo_b200.env:TinyCarloEnv'\nprint('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "tests", "golden", "gym_stub"), root]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

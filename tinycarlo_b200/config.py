@@ -68,3 +68,34 @@ def camera_params(camera_config: Dict[str, Any]) -> Dict[str, Any]:
     if not cam["max_range"]:
         raise ValueError("camera.max_range must be a positive number (the reference raises on the first frame when it is None)")
     return cam
+
+
+# ------------------------------------------------------------------------------------------------ shipped configurations
+# The car / camera sections of examples/config_knuffingen.yaml and config_simple_layout.yaml, and the spawn points they
+# list, as dict configs over the maps bundled in tinycarlo_b200/maps/ (benchmarks, tools and tests build theirs from these).
+CAR_SHIPPED = {"wheelbase": 0.0487, "track_width": 0.027, "max_velocity": 0.1, "max_steering_angle": 30, "steering_speed": 30,
+               "max_acceleration": 0.1, "max_deceleration": 1.0}
+CAM_SHIPPED = {"position": [0.0, -0.005, 0.04], "orientation": [22, 0, 0], "resolution": [128, 160], "fov": 80, "max_range": 0.5,
+               "line_thickness": 2}
+SPAWN_KNUFF = [156, 18, 217, 214, 325, 354, 176, 402, 339, 376, 385, 419, 396, 37, 149, 62, 240, 113, 98, 299, 2]
+SPAWN_SIMPLE = [57, 143, 112, 121, 138, 157, 67, 46, 165, 124, 79, 33, 84, 21, 178, 7]
+PPM = {"knuffingen": 222, "simple_layout": 450, "formula_student_track": 300, "formula_student_skidpad": 200}
+
+
+def make_config(map_name: str, fmt: str, car: Optional[Dict[str, Any]] = None, cam: Optional[Dict[str, Any]] = None, spawn="default",
+                fps: int = 30) -> Dict[str, Any]:
+    """Dict config on a bundled map: the shipped car / camera sections with `car` / `cam` overrides. spawn: "default" (the
+    yaml's spawn_points for knuffingen / simple_layout), None (any node with a successor, map.py:51-69) or a node list."""
+    car_cfg = dict(CAR_SHIPPED)
+    car_cfg.update(car or {})
+    cam_cfg = {k: (list(v) if isinstance(v, list) else v) for k, v in CAM_SHIPPED.items()}
+    cam_cfg.update(cam or {})
+    map_cfg = {"map_name": map_name, "pixel_per_meter": PPM[map_name]}
+    if spawn == "default":
+        if map_name == "knuffingen":
+            map_cfg["spawn_points"] = list(SPAWN_KNUFF)
+        elif map_name == "simple_layout":
+            map_cfg["spawn_points"] = list(SPAWN_SIMPLE)
+    elif spawn is not None:
+        map_cfg["spawn_points"] = list(spawn)
+    return {"sim": {"fps": fps, "observation_space_format": fmt}, "car": car_cfg, "camera": cam_cfg, "map": map_cfg}

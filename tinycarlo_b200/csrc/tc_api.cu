@@ -90,6 +90,7 @@ struct TcHandle {
     bool cull_built_once = false;
     int cull_cells = 0, cull_max_nodes = 0;
     uint8_t *ar_done = nullptr; // autoreset flags: caller-owned device buffer
+    uint8_t *ar_was_reset = nullptr; // optional: which envs the last step reset (caller-owned)
     uint64_t *rng = nullptr;    // spawn streams: caller-owned device buffers
     const int32_t *spawn_points = nullptr;
     int n_spawn_points = 0;
@@ -170,6 +171,10 @@ static int tc_install_cull(TcHandle *h, double radius) {
 extern "C" {
 
 int tc_abi_version(void) { return TC_ABI_VERSION; }
+#ifndef TC_SRC_HASH
+#define TC_SRC_HASH "unknown"
+#endif
+const char *tc_build_info(void) { return TC_SRC_HASH; }
 const char *tc_last_error(void) { return g_last_error.c_str(); }
 
 int tc_destroy(TcHandle *h) {
@@ -403,6 +408,12 @@ int tc_set_autoreset(TcHandle *h, uint8_t *dev_done) {
     return TC_OK;
 }
 
+int tc_set_reset_mask(TcHandle *h, uint8_t *dev_was_reset) {
+    if (!h) return tc_fail(TC_ERR_INVALID, "tc_set_reset_mask: null handle");
+    h->ar_was_reset = dev_was_reset;
+    return TC_OK;
+}
+
 int tc_set_spawn_rng(TcHandle *h, uint64_t *dev_rng_state, const int32_t *dev_spawn_points, int32_t n_spawn_points, int32_t *dev_last_spawn) {
     if (!h) return tc_fail(TC_ERR_INVALID, "tc_set_spawn_rng: null handle");
     if (n_spawn_points < 0 || (n_spawn_points > 0 && !dev_spawn_points)) return tc_fail(TC_ERR_INVALID, "tc_set_spawn_rng: bad spawn_points");
@@ -516,7 +527,7 @@ static int tc_launch_track(TcHandle *h, int mode, const float *cc, const int32_t
     ta.act_cc = cc; ta.act_cc64 = cc64; ta.act_man = man; ta.mask = mask; ta.spawn_nodes = spawn;
     ta.near_x0 = h->near_h.x0; ta.near_y0 = h->near_h.y0; ta.near_inv_cell = h->near_h.inv_cell; ta.near_nx = h->near_h.nx; ta.near_ny = h->near_h.ny;
     ta.near_off = h->d_near_off; ta.near_edge = h->d_near_edge;
-    ta.done = h->ar_done; ta.rng = h->rng; ta.spawn_points = h->spawn_points; ta.n_spawn_points = h->n_spawn_points; ta.last_spawn = h->last_spawn;
+    ta.done = h->ar_done; ta.was_reset = h->ar_done ? h->ar_was_reset : nullptr; ta.rng = h->rng; ta.spawn_points = h->spawn_points; ta.n_spawn_points = h->n_spawn_points; ta.last_spawn = h->last_spawn;
     if (outs) ta.out = *outs;
     const int envs_per_block = TC_TRACK_THREADS / 32;
     tc_track_kernel<<<(h->n_envs + envs_per_block - 1) / envs_per_block, TC_TRACK_THREADS, h->track_smem, st>>>(ta);
@@ -610,7 +621,15 @@ int tc_set_state(TcHandle *h, const double *dev_sf, const int32_t *dev_si, void 
 
 int tc_step_host(TcHandle *h, const float *host_car_control, const int32_t *host_maneuver, const TcOutputs *dev_outs, float *host_reward,
                  uint8_t *host_terminated, uint8_t *host_truncated, float *host_cte, float *host_heading_error, void *stream) {
+    return tc_step_host_obs(h, host_car_control, host_maneuver, dev_outs, host_reward, host_terminated, host_truncated, host_cte,
+                            host_heading_error, nullptr, 0, stream);
+}
+
+int tc_step_host_obs(TcHandle *h, const float *host_car_control, const int32_t *host_maneuver, const TcOutputs *dev_outs, float *host_reward,
+                     uint8_t *host_terminated, uint8_t *host_truncated, float *host_cte, float *host_heading_error, void *host_obs,
+                     size_t obs_bytes, void *stream) {
     if (!h || !host_car_control || !host_maneuver) return tc_fail(TC_ERR_INVALID, "tc_step_host: null argument");
+    if (host_obs && !(dev_outs && dev_outs->obs)) return tc_fail(TC_ERR_INVALID, "tc_step_host_obs: host_obs needs dev_outs->obs (the device frame buffer)");
     TC_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t N = (size_t)h->n_envs;
@@ -629,6 +648,7 @@ int tc_step_host(TcHandle *h, const float *host_car_control, const int32_t *host
     if (host_truncated) TC_CUDA(cudaMemcpyAsync(host_truncated, o.truncated, N, cudaMemcpyDeviceToHost, st));
     if (host_cte) TC_CUDA(cudaMemcpyAsync(host_cte, o.cte, N * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (host_heading_error) TC_CUDA(cudaMemcpyAsync(host_heading_error, o.heading_error, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (host_obs && obs_bytes) TC_CUDA(cudaMemcpyAsync(host_obs, o.obs, obs_bytes, cudaMemcpyDeviceToHost, st));   // ONE copy for all envs
     TC_CUDA(cudaStreamSynchronize(st));
     return TC_OK;
 }

@@ -49,7 +49,11 @@ TC_HD void tc_group_argmin(const TcLanes &g, double &d, int &idx) {
 
 // ------------------------------------------------------------------------------------------------ small math
 // helper.py:11-19
+// (the reference's loops never end for +-inf and take |a|/2pi rounds: angles on this path are sums of a few values in
+// [-pi, pi] and maneuver * pi/2, so anything beyond 1e4 rad is a non-finite or corrupt input and comes back as NaN,
+// which every comparison downstream treats as "no")
 TC_HD double tc_clip_angle(double a) {
+    if (!(fabs(a) <= 1.0e4)) return NAN;
     while (a > TC_PI) a -= 2 * TC_PI;
     while (a < -TC_PI) a += 2 * TC_PI;
     return a;
@@ -59,8 +63,9 @@ TC_HD double tc_dist(double ax, double ay, double bx, double by) {
     double dx = ax - bx, dy = ay - by;
     return sqrt(dx * dx + dy * dy);
 }
-// np.clip on float64 scalars
+// np.clip on float64 scalars (NaN propagates, as in numpy)
 TC_HD double tc_np_clip(double x, double lo, double hi) {
+    if (x != x) return x;
     double m = x > lo ? x : lo;
     return m < hi ? m : hi;
 }
@@ -89,6 +94,7 @@ struct TcTrackTables {
     const int32_t *ll_edge_off;  // [C+1]
     const float *ll_nodes32;     // [sumN][2] float copy of ll_nodes for the pre-filter of the nearest-edge scan
     double scan_margin;          // 2*eps of the float pre-filter (metres)
+    double scan_limit;           // |x|, |y| up to which that margin is proven; farther out the scan is plain float64
     // nearest-laneline index (tc_cull.h tc_build_near; global memory, optional): per (class, ground cell) the edges that can
     // be the arg-min of d(p,n0)+d(p,n1) for a p inside the cell, ascending
     double near_x0, near_y0, near_inv_cell;
@@ -103,7 +109,7 @@ struct TcBlobLayout {
     int32_t off_lp_nodes, off_lp_orient, off_lp_orient_rev, off_ll_nodes, off_lp_edges, off_next_off, off_next_edge, off_prev_off,
         off_prev_edge, off_ll_edges, off_ll_node_off, off_ll_edge_off, off_ll_nodes32;
     int32_t total_bytes;
-    double scan_margin;
+    double scan_margin, scan_limit;
 };
 
 TC_HD TcTrackTables tc_track_tables(const unsigned char *base, const TcBlobLayout &L) {
@@ -125,6 +131,7 @@ TC_HD TcTrackTables tc_track_tables(const unsigned char *base, const TcBlobLayou
     t.ll_edge_off = (const int32_t *)(base + L.off_ll_edge_off);
     t.ll_nodes32 = (const float *)(base + L.off_ll_nodes32);
     t.scan_margin = L.scan_margin;
+    t.scan_limit = L.scan_limit;
     t.near_x0 = t.near_y0 = t.near_inv_cell = 0.0;
     t.near_nx = t.near_ny = 0;
     t.near_off = nullptr; t.near_edge = nullptr;
@@ -282,6 +289,8 @@ TC_HD void tc_store_state(double *sf, int32_t *si, const TcCarState &s) {
 
 // car.py:127-148. Group-uniform control flow; only the u-turn scan is spread over the lanes. Returns truncated.
 TC_HD bool tc_find_local_path(const TcLanes &g, const TcTrackTables &t, TcCarState &s, int maneuver) {
+    // an env that was never reset (or whose reset found no successor edge) has no tracked edge: truncated, tables untouched
+    if (s.path_len <= 0 || s.pe[0] < 0 || s.pe[0] >= t.lp_n_edges || s.pn[0] < 0 || s.pn[1] < 0) return true;
     double dir = tc_clip_angle(t.lp_orient[s.pe[0]] + maneuver * TC_PI / 2);
     int ne; // new first edge
     if (maneuver == 2 && s.last_man != 2) {
@@ -403,7 +412,9 @@ TC_HD TcInfo tc_get_info(const TcLanes &g, const TcTrackTables &t, const double 
             if (cell >= 0) {
                 const int32_t *o = t.near_off + (size_t)c * t.near_nx * t.near_ny + cell;
                 e = tc_nearest_edge_list(g, nodes, edges, t.near_edge + o[0], o[1] - o[0], s.x, s.y);
-            } else e = tc_nearest_edge_prefiltered(g, nodes, t.ll_nodes32 + 2 * t.ll_node_off[c], edges, m, s.x, s.y, t.scan_margin);
+            } else if (fabs(s.x) <= t.scan_limit && fabs(s.y) <= t.scan_limit)
+                e = tc_nearest_edge_prefiltered(g, nodes, t.ll_nodes32 + 2 * t.ll_node_off[c], edges, m, s.x, s.y, t.scan_margin);
+            else e = tc_nearest_edge(g, nodes, edges, m, s.x, s.y, nullptr, 0, 0);   // a runaway car (wrapped envs never terminate): no pre-filter
             nearest[c] = e;
             if (e < 0) continue; // class without edges: the reference would raise on min([])
             int n0 = edges[2 * e], n1 = edges[2 * e + 1];

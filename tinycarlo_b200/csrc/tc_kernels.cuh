@@ -74,6 +74,7 @@ struct TcTrackArgs {
     const int32_t *spawn_nodes; // reset
     // next-step autoreset (gymnasium AutoresetMode.NEXT_STEP): an env whose previous step ended is reset by this step
     uint8_t *done;              // [N] in/out, NULL = autoreset off
+    uint8_t *was_reset;         // [N] out, optional: 1 when this step reset the env instead of stepping it
     // spawn draws on the device (tc_set_spawn_rng): per-env PCG64 state, optional spawn_points list, last node drawn
     uint64_t *rng;              // [N, TC_RNG_N]
     const int32_t *spawn_points;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS, 3) tc_track_kernel(const TcT
     if (auto_reset) { info.reward = 0; info.terminated = false; }
     if (g.lane != 0) return;
     if (a.mode == 0 && a.done) a.done[env] = (info.terminated || truncated) ? 1 : 0;
+    if (a.mode == 0 && a.was_reset) a.was_reset[env] = auto_reset ? 1 : 0;
     tc_store_state(sf, si, s);
     // pose for the camera pass: front-axle update already evaluated cos/sin(rot); recomputing keeps the code simple
     tc_camera_pose(a.cam + (size_t)env * TC_CAM_N + TC_CAM_E, s.x, s.y, cos(s.rot), sin(s.rot), a.pose + (size_t)env * 12);

@@ -79,6 +79,7 @@ static inline std::string tc_pack_map(const TcMapDesc *map, TcPacked &pk) {
         for (int i = 0; i < 2 * sumN; i++) { f32[i] = (float)map->ll_nodes[i]; ext = std::max(ext, std::fabs(map->ll_nodes[i])); }
         for (int i = 0; i < 2 * P; i++) ext = std::max(ext, std::fabs(map->lp_nodes[i]));
         L.scan_margin = 1e-4 * (4.0 * ext);   // car positions may leave the map: allow 4x the map extent
+        L.scan_limit = 4.0 * ext;             // beyond it the tracking kernel scans in plain float64 (tc_get_info)
     }
     // laneline node adjacency per class, in edge order (the clip passes apply a node's edges in list order)
     pk.adj_base.resize(C);

@@ -15,6 +15,19 @@ def shard_range(total_envs: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def shard_groups(group_sizes, rank: int, world: int):
+    """Resolution groups (TinyCarloGroupedVecEnv) of a multi-GPU job: every rank takes a contiguous slice of EVERY group.
+    group_sizes: global envs per group (group g owns the global indices [sum(sizes[:g]), sum(sizes[:g+1]))).
+    -> (local sizes, global index of each local group's env 0): pass them as the group sizes and group_index_offsets."""
+    sizes, offsets, base = [], [], 0
+    for n in group_sizes:
+        lo, hi = shard_range(int(n), rank, world)
+        sizes.append(hi - lo)
+        offsets.append(base + lo)
+        base += int(n)
+    return sizes, offsets
+
+
 class EpisodeStats:
     """Per-rank running episode statistics on the device: episodes finished, truncations, reward sum, env-steps."""
     FIELDS = ("episodes", "truncated", "reward_sum", "env_steps")

@@ -172,6 +172,8 @@ class TinyCarloEnv(gc.Env):
         if not self._vec._seeded:
             self._vec._seed(0)   # the single env draws on the host generator gymnasium seeded; the device stream stays unused
         self._vec.reset(spawn_nodes=torch.tensor([node], dtype=torch.int32))
+        if self.render_mode == "human":   # env.py:109-110: the reference shows its windows from reset() and step()
+            self.render()
         return self._obs(), self._info()
 
     def step(self, action: Dict[str, Any]) -> Tuple[np.ndarray, float, bool, bool, Dict[str, Any]]:
@@ -182,6 +184,8 @@ class TinyCarloEnv(gc.Env):
         _, reward, terminated, truncated, _ = self._vec.step({"car_control": self._cc, "maneuver": self._man})
         i64 = self._vec.out["info_f64"][0, 3].item()
         rew = float(i64) if not self._wrapped else 0
+        if self.render_mode == "human":   # env.py:140-141
+            self.render()
         return self._obs(), rew, bool(terminated[0].item()), bool(truncated[0].item()), self._info()
 
     def render_overview(self) -> np.ndarray:

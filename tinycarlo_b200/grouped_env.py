@@ -18,8 +18,11 @@ class TinyCarloGroupedVecEnv:
     is_vector_env = True
 
     def __init__(self, config: Union[str, Dict[str, Any]], groups: Sequence[Tuple[int, Sequence[int]]], device="cuda",
-                 env_index_offset: int = 0, **kw):
-        """groups: [(num_envs, [H, W]), ...]. Other arguments as TinyCarloVecEnv."""
+                 env_index_offset: int = 0, group_index_offsets: Optional[Sequence[int]] = None, overlap: bool = True, **kw):
+        """groups: [(num_envs, [H, W]), ...]. group_index_offsets: global index of each group's env 0 (default: the groups follow
+        each other from env_index_offset on); a multi-GPU job gives every rank a contiguous slice of EVERY group
+        (distributed.shard_groups), so that env seeds and per-env parameters do not depend on the sharding. overlap: enqueue
+        the groups on separate streams (False: one after the other on the caller's stream). Other arguments as TinyCarloVecEnv."""
         cfg, path = load_config(config)
         self.envs: List[TinyCarloVecEnv] = []
         self.offsets = [0]
@@ -29,13 +32,15 @@ class TinyCarloGroupedVecEnv:
             if path is not None and "json_path" in c["map"]:   # keep json_path relative to the yaml's directory
                 import os
                 c["map"]["json_path"] = os.path.join(os.path.dirname(path), c["map"]["json_path"])
-            self.envs.append(TinyCarloVecEnv(c, int(n), device=device, env_index_offset=env_index_offset + self.offsets[-1], **kw))
+            goff = env_index_offset + self.offsets[-1] if group_index_offsets is None else int(group_index_offsets[len(self.envs)])
+            self.envs.append(TinyCarloVecEnv(c, int(n), device=device, env_index_offset=goff, **kw))
             self.offsets.append(self.offsets[-1] + int(n))
         self.num_envs = self.offsets[-1]
         self.device = self.envs[0].device
         self.class_names = self.envs[0].class_names
         self.track_width = self.envs[0].track_width
         self.autoreset = self.envs[0].autoreset
+        self.overlap = bool(overlap)
         self._streams = [torch.cuda.Stream(device=self.device) for _ in self.envs]
 
     @property
@@ -47,6 +52,8 @@ class TinyCarloGroupedVecEnv:
 
     def _fan_out(self, fn):
         """run fn(env, slice) for every group on its own stream, ordered after the caller's stream and joined back"""
+        if not self.overlap:
+            return [fn(env, sl) for env, sl in zip(self.envs, self._slices())]
         cur = torch.cuda.current_stream(self.device)
         start = torch.cuda.Event()
         start.record(cur)
@@ -113,6 +120,18 @@ class TinyCarloGroupedVecEnv:
                     v = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
                     sub[k] = v[a:b]
             e.set_car_params(**sub)
+
+    @property
+    def launch_count(self) -> int:
+        return sum(e.launch_count for e in self.envs)
+
+    @property
+    def reset_mask(self) -> torch.Tensor:
+        return torch.cat([e.reset_mask for e in self.envs])
+
+    @property
+    def obs_bytes_per_step(self) -> int:
+        return sum(e.obs.numel() * e.obs.element_size() for e in self.envs)
 
     def close(self):
         for e in self.envs:

@@ -10,7 +10,8 @@ and no CPU implementation.
 Returned tensors are owned by the env and are overwritten by the next step()/reset(); clone what must survive.
 """
 import ctypes as C
-from typing import Any, Dict, Optional, Union
+import os
+from typing import Any, Callable, Dict, Optional, Union
 
 import numpy as np
 import torch
@@ -108,6 +109,7 @@ class TinyCarloVecEnv:
         cc = self.cam_cfg
         self._cam_rows = np.tile(camera_row(cc["position"], cc["orientation"], cc["fov"], cc["resolution"], cc["max_range"]), (N, 1))
         self._thickness = np.full(N, int(cc["line_thickness"]), np.int32)
+        self._check_car_rows(self._car_rows)
         self._upload_params()
 
         # ---- spawn draws (map.py:51-69) on the device: one numpy-compatible PCG64 stream per env, seeded like gymnasium
@@ -121,11 +123,18 @@ class TinyCarloVecEnv:
             sp = self.map.spawn_points
             self._spawn_points = None if sp is None else torch.tensor(sp, dtype=torch.int32, device=dev)
             self.done_flags = torch.zeros(N, dtype=torch.uint8, device=dev) if autoreset else None
+            # autoreset: which envs the latest step() reset instead of advancing (all zero otherwise)
+            self._reset_mask = torch.zeros(N, dtype=torch.uint8, device=dev)
         _lib.check(self._L.tc_set_spawn_rng(self._h, _ptr(self._rng_state), _ptr(self._spawn_points), 0 if sp is None else len(sp),
                                             _ptr(self._spawn_nodes)), "tc_set_spawn_rng")
         if autoreset:
             _lib.check(self._L.tc_set_autoreset(self._h, _ptr(self.done_flags)), "tc_set_autoreset")
+            _lib.check(self._L.tc_set_reset_mask(self._h, _ptr(self._reset_mask)), "tc_set_reset_mask")
         self._seeded = False
+        self._was_reset = False   # step() before the first reset() raises (the reference resets in its constructor)
+        # tinycarlo/helper.py:4 getenv("DEBUG"): per-phase milliseconds printed after every step (env.py:144-145); here the
+        # phases are the two kernels, timed with CUDA events - this mode synchronises, the normal one never does
+        self._debug = os.environ.get("DEBUG", "").lower() == "1"
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def _make_outputs(self, with_obs: bool) -> _lib.TcOutputs:
@@ -171,14 +180,31 @@ class TinyCarloVecEnv:
         reference allows it (steering_speed, max_acceleration). Keys as in the config's `car` section."""
         cols = {"wheelbase": 0, "track_width": 1, "max_velocity": 2, "max_steering_angle": 3, "steering_speed": 4,
                 "max_acceleration": 5, "max_deceleration": 6}
+        rows = self._car_rows.copy()
         for key, val in kw.items():
             col = cols[key]
             if val is None:
-                self._car_rows[:, col] = np.nan
+                if key not in ("steering_speed", "max_acceleration"):
+                    raise ValueError(f"car.{key} cannot be None")
+                rows[:, col] = np.nan
             else:
                 v = val.detach().cpu().numpy() if isinstance(val, torch.Tensor) else np.asarray(val, np.float64)
-                self._car_rows[:, col] = v
+                rows[:, col] = v
+        self._check_car_rows(rows)
+        self._car_rows = rows
         self._upload_params()
+
+    @staticmethod
+    def _check_car_rows(rows: np.ndarray):
+        """Rejects parameters that make the bicycle model degenerate (wheelbase 0 divides by zero in car.py:103, a non-finite
+        value poisons every env that reads it); the reference accepts them and produces inf / NaN poses."""
+        for col, name, positive in ((0, "wheelbase", True), (1, "track_width", True), (2, "max_velocity", False),
+                                    (3, "max_steering_angle", False), (6, "max_deceleration", False), (7, "dt", True)):
+            v = rows[:, col]
+            if name == "max_deceleration":
+                v = v[~np.isnan(rows[:, 5])]   # only read when max_acceleration is set (car.py:81-82)
+            if not np.all(np.isfinite(v)) or (positive and not np.all(v > 0)):
+                raise ValueError(f"car.{name} must be finite" + (" and > 0" if positive else ""))
 
     def set_camera_params(self, position=None, orientation=None, fov=None, max_range=None, line_thickness=None, env_ids=None):
         """Per-env camera parameters (camera.py:48-50 update_params, vectorised). Arrays are [n,3] / [n] for the envs in
@@ -254,6 +280,7 @@ class TinyCarloVecEnv:
                 self.done_flags.masked_fill_(mask_u8.bool(), 0)
             outs = self._outs if not self.no_observation else self._outs_noobs
             _lib.check(self._L.tc_reset(self._h, _ptr(mask_u8), _ptr(nodes), C.byref(outs), self._stream()), "tc_reset")
+            self._was_reset = True
         return self.obs, self._info()
 
     def step(self, action: Dict[str, torch.Tensor]):
@@ -261,21 +288,60 @@ class TinyCarloVecEnv:
         int [N]. Returns (obs, reward f32[N], terminated bool[N], truncated bool[N], info dict of tensors)."""
         cc = action["car_control"]
         man = action["maneuver"]
+        if cc.dtype not in (torch.float32, torch.float64):
+            cc = cc.to(torch.float32)
+        cc = cc.contiguous()              # keeps the dtype: a float64 slice stays on the float64 entry point
         f64 = cc.dtype == torch.float64   # float64 actions keep the reference's float64 path bit for bit
-        if (cc.dtype not in (torch.float32, torch.float64)) or not cc.is_contiguous():
-            cc = cc.to(torch.float32).contiguous()
         if man.dtype != torch.int32 or not man.is_contiguous():
             man = man.to(torch.int32).contiguous()
         if cc.device != self.device or man.device != self.device or cc.shape != (self.num_envs, 2) or man.shape != (self.num_envs,):
             raise ValueError("action tensors must live on the env's device with shapes [N,2] and [N]")
         outs = self._outs if not self.no_observation else self._outs_noobs
         with torch.cuda.device(self.device):
-            if self.autoreset and not self._seeded:
+            if not self._was_reset:
                 raise _lib.TinyCarloError("call reset() before step()")
             fn = self._L.tc_step_f64 if f64 else self._L.tc_step
+            dbg = self._debug and not torch.cuda.is_current_stream_capturing()
+            if dbg:
+                self.profile_begin(1)
             _lib.check(fn(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
+            if dbg:
+                ms, _ = self.profile_end()
+                print(f"all: {ms['track'] + ms['project'] + ms['raster']:.3f} ms | obs render {ms['project'] + ms['raster']:.3f} ms | "
+                      f"car step + info {ms['track']:.3f} ms  ({self.num_envs} envs)")
         o = self.out
         return self.obs, o["reward"], o["terminated"].view(torch.bool), o["truncated"].view(torch.bool), self._info()
+
+    def capture(self, policy_fn: Optional[Callable[["TinyCarloVecEnv"], Dict[str, torch.Tensor]]] = None, steps: int = 1,
+                warmup: int = 3) -> "torch.cuda.CUDAGraph":
+        """Captures `steps` iterations of `action = policy_fn(env); env.step(action)` in a CUDA graph and returns it; every
+        graph.replay() then advances all envs by `steps` steps with a single launch (step() neither allocates nor synchronises,
+        and resets happen inside the kernels with autoreset="next_step"). policy_fn must only enqueue work on the current
+        stream and write into tensors it owns; results are read from env.obs / env.out afterwards. The launch-bound small
+        configurations (BASELINE config 2: 4096 envs at 84x84) gain the most. The warm-up steps and the captured call itself
+        do advance / not advance the envs respectively, as torch's capture rules imply."""
+        if self.autoreset is None and steps > 1:
+            raise ValueError("capturing several steps needs autoreset='next_step' (nothing else resets finished envs inside a graph)")
+        if not self._was_reset:
+            raise _lib.TinyCarloError("call reset() before capture()")
+        dbg, self._debug = self._debug, False
+
+        def one():
+            if policy_fn is None:
+                raise ValueError("capture() needs a policy_fn(env) -> action dict")
+            self.step(policy_fn(self))
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                one()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(int(steps)):
+                one()
+        self._debug = dbg
+        return graph
 
     def reset_done(self):
         """Resets the envs whose last step terminated or truncated, as a caller of the reference would (on the device, no
@@ -283,18 +349,42 @@ class TinyCarloVecEnv:
         done = self.out["terminated"] | self.out["truncated"]
         return self.reset(mask=done)
 
+    @property
+    def reset_mask(self) -> torch.Tensor:
+        """bool [N]: the envs that the latest step() reset instead of advancing (autoreset="next_step"); their reward is 0,
+        their info empty and their observation the spawn frame. All False without autoreset."""
+        return self._reset_mask.view(torch.bool)
+
     def mark_done(self, mask: torch.Tensor):
         """autoreset only: ORs extra termination conditions (e.g. from wrappers) into the flags the next step() consumes."""
         self.done_flags |= mask.to(device=self.device, dtype=torch.uint8)
 
     def step_host(self, car_control: torch.Tensor, maneuver: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor,
-                  truncated: torch.Tensor, cte: Optional[torch.Tensor] = None, heading_error: Optional[torch.Tensor] = None):
+                  truncated: torch.Tensor, cte: Optional[torch.Tensor] = None, heading_error: Optional[torch.Tensor] = None,
+                  obs_host: Optional[torch.Tensor] = None):
         """The same step with HOST tensors (ideally pinned): actions are copied to the device, the scalar results copied
-        back, and the stream synchronised inside the call (tc_step_host). Observations stay on the device in self.obs."""
+        back, and the stream synchronised inside the call (tc_step_host). Observations stay on the device in self.obs unless
+        obs_host (a host tensor of self.obs's shape and dtype) is given: then all frames follow in one device-to-host copy
+        (tc_step_host_obs; use obs_format="classes_bits" to move an eighth of the bytes)."""
+        if not self._was_reset:
+            raise _lib.TinyCarloError("call reset() before step_host()")
+        for name, t, shape, dt in (("car_control", car_control, (self.num_envs, 2), torch.float32), ("maneuver", maneuver, (self.num_envs,), torch.int32)):
+            if t.is_cuda or t.dtype != dt or tuple(t.shape) != shape or not t.is_contiguous():
+                raise ValueError(f"step_host: {name} must be a contiguous host tensor of dtype {dt} and shape {shape}")
         outs = self._outs if not self.no_observation else self._outs_noobs
         with torch.cuda.device(self.device):
-            _lib.check(self._L.tc_step_host(self._h, _ptr(car_control), _ptr(maneuver), C.byref(outs), _ptr(reward), _ptr(terminated),
-                                            _ptr(truncated), _ptr(cte), _ptr(heading_error), self._stream()), "tc_step_host")
+            if obs_host is None:
+                _lib.check(self._L.tc_step_host(self._h, _ptr(car_control), _ptr(maneuver), C.byref(outs), _ptr(reward), _ptr(terminated),
+                                                _ptr(truncated), _ptr(cte), _ptr(heading_error), self._stream()), "tc_step_host")
+            else:
+                if obs_host.is_cuda or obs_host.dtype != self.obs.dtype or obs_host.shape != self.obs.shape or not obs_host.is_contiguous():
+                    raise ValueError("step_host: obs_host must be a contiguous host tensor with the shape and dtype of env.obs")
+                if self.no_observation:
+                    raise ValueError("step_host: obs_host given but no_observation is set")
+                nbytes = self.obs.numel() * self.obs.element_size()
+                _lib.check(self._L.tc_step_host_obs(self._h, _ptr(car_control), _ptr(maneuver), C.byref(outs), _ptr(reward), _ptr(terminated),
+                                                    _ptr(truncated), _ptr(cte), _ptr(heading_error), _ptr(obs_host), nbytes, self._stream()),
+                           "tc_step_host_obs")
 
     def render_rgb(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """RGB camera frames [N,H,W,3] at the current poses (renderer.py:36-44), independent of the obs format."""
@@ -362,6 +452,7 @@ class TinyCarloVecEnv:
             si = state["si"].to(device=self.device, dtype=torch.int32).contiguous()
             _lib.check(self._L.tc_set_state(self._h, _ptr(sf), _ptr(si), self._stream()), "tc_set_state")
             torch.cuda.current_stream(self.device).synchronize()
+        self._was_reset = True
 
     def profile_begin(self, max_steps: int):
         _lib.check(self._L.tc_profile_begin(self._h, int(max_steps)), "tc_profile_begin")

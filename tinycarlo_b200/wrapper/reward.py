@@ -40,6 +40,14 @@ class _VecWrapper:
     def step(self, action):
         return self.env.step(action)
 
+    def _live(self, bonus: torch.Tensor) -> torch.Tensor:
+        """the wrapper's reward term, zero for envs that this step autoreset (no transition happened: gymnasium's
+        next-step autoreset returns reward 0 there, and a caller of the reference would have called reset() instead)"""
+        u = self.unwrapped
+        if getattr(u, "autoreset", None):
+            return torch.where(u.reset_mask, torch.zeros_like(bonus), bonus)
+        return bonus
+
 
 def _make(cls_scalar, cls_vec):
     """class factory: Name(env, ...) -> scalar or vector implementation"""
@@ -76,7 +84,7 @@ class _LanelineSparseVec(_VecWrapper):
     def step(self, action):
         observation, reward, terminated, truncated, info = self.env.step(action)
         cond = info["laneline_distances"] < self.unwrapped.track_width / 2
-        reward = reward + (cond.to(torch.float32) * self._w).sum(dim=1)
+        reward = reward + self._live((cond.to(torch.float32) * self._w).sum(dim=1))
         return observation, reward, terminated, truncated, info
 
 
@@ -110,7 +118,7 @@ class _LanelineLinearVec(_VecWrapper):
         observation, reward, terminated, truncated, info = self.env.step(action)
         u = self.unwrapped
         for k, n in enumerate(u.class_names):
-            reward = reward + linear_reward_tensor(info["laneline_distances"][:, k], u.track_width, self.max_rewards[n])
+            reward = reward + self._live(linear_reward_tensor(info["laneline_distances"][:, k], u.track_width, self.max_rewards[n]))
         return observation, reward, terminated, truncated, info
 
 
@@ -141,7 +149,7 @@ class _CTESparseVec(_VecWrapper):
 
     def step(self, action):
         observation, reward, terminated, truncated, info = self.env.step(action)
-        reward = reward + (info["cte"].abs() <= self.min_cte).to(torch.float32) * self.sparse_reward
+        reward = reward + self._live((info["cte"].abs() <= self.min_cte).to(torch.float32) * self.sparse_reward)
         return observation, reward, terminated, truncated, info
 
 
@@ -170,7 +178,7 @@ class _CTELinearVec(_VecWrapper):
 
     def step(self, action):
         observation, reward, terminated, truncated, info = self.env.step(action)
-        reward = reward + linear_reward_tensor(info["cte"], self.min_cte, self.max_reward, self.min_reward)
+        reward = reward + self._live(linear_reward_tensor(info["cte"], self.min_cte, self.max_reward, self.min_reward))
         return observation, reward, terminated, truncated, info
 
 

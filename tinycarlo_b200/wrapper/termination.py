@@ -41,6 +41,8 @@ class _LanelineCrossingVec(_VecWrapper):
         observation, reward, terminated, truncated, info = self.env.step(action)
         u = self.unwrapped
         hit = (info["laneline_distances"][:, self._cols] <= u.track_width / 2).any(dim=1)
+        if getattr(u, "autoreset", None):
+            hit = hit & ~u.reset_mask   # the empty info of a reset step (all distances 0) is not a crossing
         terminated = terminated | hit
         _feed_autoreset(self, terminated)
         return observation, reward, terminated, truncated, info
@@ -84,7 +86,14 @@ class _CounterVec(_VecWrapper):
 
     def _update(self, cond: torch.Tensor, terminated: torch.Tensor) -> torch.Tensor:
         cnt = torch.where(cond, self.steps_true + 1, torch.zeros_like(self.steps_true))
-        fire = cnt >= self.number_of_steps
+        u = self.unwrapped
+        if getattr(u, "autoreset", None):
+            # a step that reset the env is not a step of the wrapped env (a caller of the reference calls reset() there,
+            # which leaves steps_true alone)
+            cnt = torch.where(u.reset_mask, self.steps_true, cnt)
+            fire = (cnt >= self.number_of_steps) & ~u.reset_mask
+        else:
+            fire = cnt >= self.number_of_steps
         self.steps_true = torch.where(fire, torch.zeros_like(cnt), cnt)
         terminated = terminated | fire
         _feed_autoreset(self, terminated)
