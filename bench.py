@@ -597,9 +597,9 @@ def obs_to_host_leg(w, dev, args, max_steer):
     cfg = make_config(w["map"], w["fmt"], car=w["car"], cam={"resolution": w["res"]})
     try:
         env = TinyCarloVecEnv(cfg, n, device=dev, autoreset="next_step", obs_format="classes_bits")
-    except Exception as e:   # e.g. H*W not a multiple of 32
+        env.reset(seed=0)
+    except Exception as e:   # e.g. H*W not a multiple of 32 (84x84)
         return {"unavailable": str(e)}
-    env.reset(seed=0)
     pin = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt).pin_memory()   # noqa: E731
     h_obs = torch.zeros(env.obs.shape, dtype=env.obs.dtype).pin_memory()
     hs = [pin(n, 2), pin(n, dt=torch.int32), pin(n), pin(n, dt=torch.uint8), pin(n, dt=torch.uint8), pin(n), pin(n)]
