@@ -199,6 +199,10 @@ TC_API int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline);
  * cell. tc_set_camera_params rebuilds the tables (and synchronises the stream) when the cameras' reach changes. Setting
  * the environment variable TC_CULL=0 switches the culling off. */
 TC_API int tc_debug_cull_info(TcHandle *h, double *host_out4);
+/* Diagnostics: which kernels this handle launches. out8 = {block-per-env render path (0/1), envs per block of the packed
+ * kernel (0: one-env kernel), its 32-segment chunks, dynamic shared memory of the render kernel, thread-per-env tracking (0/1),
+ * shared memory of the banded kernel (0: unused), node capacity and table bytes of the visible-set cells}. */
+TC_API int tc_debug_render_info(TcHandle *h, int32_t *out8);
 
 /* Test hook: the reference's Layer queries (layer.py) evaluated by the DEVICE functions on class 0 of the handle's map.
  * op: 0 get_nearest_edge(pos) 1 get_nearest_edge_with_orientation(pos, a) 2 is_position_within_edge_bounds(pos, e=(i0,i1))

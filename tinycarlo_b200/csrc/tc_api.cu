@@ -65,6 +65,7 @@ struct TcHandle {
     size_t track_smem = 0, proj_smem = 0, render_smem = 0;
     int max_edges = 0, plane_words_full = 0;
     int stagger_ns = 0, n_sms = 148;
+    int track_per_thread = 1;   // tc_track_thread_kernel (one thread per env) instead of tc_track_kernel (a warp per env)
     long long *timeline = nullptr;
     bool fused_ok = false;
     int render_threads = 256;
@@ -84,6 +85,9 @@ struct TcHandle {
     TcCullGrid cull_grid{};
     int env_np = 0, env_max_bytes = 0, env_words = 0;
     size_t env_smem = 0;     // tc_render_env_kernel (small frames)
+    int env_blocks = 0;      // resident blocks per SM of the packed kernel as chosen (diagnostics)
+    int env_pack = 0, env_chunks = 1;   // > 0: tc_render_envs_kernel with that many envs per block
+    size_t envs_smem = 0;
     size_t envb_smem = 0;    // tc_render_env_banded_kernel (large frames, RGB / 1 bit per pixel); 0: not available
     int envb_rows = 0, envb_bands = 0, envb_words = 0, envb_on = 1;
     double cull_radius = -1.0, cull_mean_nodes = 0.0;
@@ -163,6 +167,34 @@ static int tc_install_cull(TcHandle *h, double radius) {
     cudaFree(h->d_cell_desc);
     cudaFree(h->d_cell_blob);
     h->d_cell_desc = dd; h->d_cell_blob = db;
+    {
+        // The packed small-frame kernel (tc_render_envs_kernel, 3 blocks of 256 threads per SM): E envs per block and 1 or 2
+        // 32-segment chunks of primitive slots, chosen for the most envs in flight per SM without dropping below 2 blocks per SM
+        // (fewer blocks hide the latency-bound phases worse than fuller lanes gain); E = 1 never beats tc_render_env_kernel
+        // (measured), which stays the fallback. TC_ENV_PACK=0|2|4 and TC_ENV_CHUNKS=1|2 override.
+        int pack = 0, chunks = 1;
+        if (h->fused_all) {
+            int best = 0;
+            for (int e : {2, 4})
+                for (int c : {2, 1}) {
+                    const size_t sm = tc_envs_smem_bytes(e, np, cull.max_bytes, h->env_words, c);
+                    if (sm > 200 * 1024) continue;
+                    int blocks = 0;   // what the device really keeps resident (registers, static + reserved shared memory, carve-out steps)
+                    cudaError_t oe = e == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tc_render_envs_kernel<256, TC_FMT_U8, 2>, 256, sm)
+                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tc_render_envs_kernel<256, TC_FMT_U8, 4>, 256, sm);
+                    if (oe != cudaSuccess) { cudaGetLastError(); continue; }
+                    if (blocks >= (e == 2 ? 2 : 3) && e * blocks > best) { best = e * blocks; pack = e; chunks = c; h->env_blocks = blocks; }
+                }
+            if (const char *pe = getenv("TC_ENV_PACK")) {
+                const int v = atoi(pe);
+                pack = (v == 1 || v == 2 || v == 4) ? v : 0;
+            }
+            if (const char *pc = getenv("TC_ENV_CHUNKS")) chunks = atoi(pc) == 2 ? 2 : 1;
+            if (pack && tc_envs_smem_bytes(pack, np, cull.max_bytes, h->env_words, chunks) > 200 * 1024) pack = 0;
+        }
+        h->env_pack = pack; h->env_chunks = chunks;
+        h->envs_smem = pack ? tc_envs_smem_bytes(pack, np, cull.max_bytes, h->env_words, chunks) : 0;
+    }
     h->cull_grid = cull.grid; h->env_np = (int)np; h->env_max_bytes = cull.max_bytes; h->env_smem = smem; h->envb_smem = smem_b;
     h->cull_radius = cull.radius; h->cull_mean_nodes = cull.mean_nodes; h->cull_cells = (int)cull.desc.size(); h->cull_max_nodes = cull.max_nodes;
     return TC_OK;
@@ -320,7 +352,9 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
         tc_build_cull(map, -1.0, 0.25, 0.05, whole);
         const size_t smem_all = tc_env_smem_bytes(tc_env_np(whole.max_nodes, whole.max_edges), whole.max_bytes, words_all);
         const size_t smem_one = tc_render_smem_bytes(h->max_nodes, h->max_edges, h->max_cblob_bytes, h->plane_words_full);
-        bool all = smem_all <= 100 * 1024 && (size_t)C * h->H * h->W <= 128 * 1024;
+        // measured (Knuffingen 240x320, 8192 envs): block per env 0.56 ms against 1.05 ms for the per-class blocks, which pay the
+        // camera pass and the set-up once per class; beyond ~75 KB a block (3 per SM) the per-class kernel's finer blocks win again
+        bool all = smem_all <= 100 * 1024 && tc_env_smem_bytes(tc_env_np(whole.max_nodes, whole.max_edges), whole.max_bytes, words_all) <= 76 * 1024;
         if (const char *fa = getenv("TC_FUSED_ALL")) all = atoi(fa) != 0 && smem_all <= 200 * 1024;
         h->fused_all = all ? 1 : 0;
         h->fused_nodes = h->max_nodes; h->fused_edges = h->max_edges;
@@ -334,7 +368,6 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
             if (const char *on = getenv("TC_ENV_BANDED")) h->envb_on = atoi(on) != 0;
         }
         h->fused_ok = all || smem_one <= 56 * 1024; // >= 4 blocks per SM; larger frames take the banded two-kernel path
-        TC_TRYH(tc_install_cull(h, -1.0));   // the whole graph until the camera parameters are known
     }
 #define TC_PREP_RENDER(K)                 \
     TC_CUDAH(tc_allow_max_smem(K));       \
@@ -348,15 +381,24 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
         TC_PREP_RENDER((tc_render_env_kernel<256, TC_FMT_RGB>));
         TC_PREP_RENDER((tc_render_env_kernel<256, TC_FMT_BITS>));
         TC_PREP_RENDER((tc_render_env_kernel<256, TC_FMT_BF16>));
+#define TC_PREP_ENVS(F) TC_PREP_RENDER((tc_render_envs_kernel<256, F, 1>)); TC_PREP_RENDER((tc_render_envs_kernel<256, F, 2>)); TC_PREP_RENDER((tc_render_envs_kernel<256, F, 4>))
+        TC_PREP_ENVS(TC_FMT_U8); TC_PREP_ENVS(TC_FMT_RGB); TC_PREP_ENVS(TC_FMT_BITS); TC_PREP_ENVS(TC_FMT_BF16);
+#undef TC_PREP_ENVS
         TC_PREP_RENDER((tc_render_classes_kernel<256, TC_FMT_U8>));
         TC_PREP_RENDER((tc_render_classes_kernel<256, TC_FMT_BITS>));
         TC_PREP_RENDER((tc_render_classes_kernel<256, TC_FMT_BF16>));
     }
 #undef TC_PREP_RENDER
+    TC_TRYH(tc_install_cull(h, -1.0));   // the whole graph until the camera parameters are known (after the kernels' attributes: it asks for occupancies)
     TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_rgb_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(tc_allow_max_smem(tc_track_kernel));
+    TC_CUDAH(tc_allow_max_smem(tc_track_thread_kernel));
+    TC_CUDAH(cudaFuncSetAttribute(tc_track_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // a warp per env pays off only when there are too few envs to fill the SMs with one thread each (TC_TRACK_MODE=warp|thread overrides)
+    h->track_per_thread = num_envs >= 8192 ? 1 : 0;   // measured: 4096 envs 0.045 (warp) vs 0.062 ms (thread), 32768 envs 0.187 vs 0.044 ms
+    if (const char *tm = getenv("TC_TRACK_MODE")) h->track_per_thread = (tm[0] == 't' || tm[0] == '1') ? 1 : 0;
     TC_CUDAH(tc_allow_max_smem(tc_project_kernel));
     TC_CUDAH(tc_allow_max_smem(tc_raster_classes_kernel));
     TC_CUDAH(tc_allow_max_smem(tc_raster_rgb_kernel));
@@ -446,6 +488,26 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
         ea.timeline = mask ? nullptr : h->timeline;
         if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
         const size_t sm = h->env_smem;
+        if (h->env_pack > 0 && !ea.timeline) {
+            const int E = h->env_pack, grid = (N + E - 1) / E;
+            const size_t sme = h->envs_smem;
+            ea.region_bytes = (int)tc_envs_region_bytes((size_t)h->env_np, h->env_max_bytes, h->env_words);
+            ea.prim_chunks = h->env_chunks;
+#define TC_LAUNCH_ENVS(F)                                                                             \
+    do {                                                                                              \
+        if (E == 4) tc_render_envs_kernel<256, F, 4><<<grid, 256, sme, st>>>(ea);                     \
+        else if (E == 2) tc_render_envs_kernel<256, F, 2><<<grid, 256, sme, st>>>(ea);                \
+        else tc_render_envs_kernel<256, F, 1><<<grid, 256, sme, st>>>(ea);                            \
+    } while (0)
+            if (obs_format == TC_OBS_RGB) TC_LAUNCH_ENVS(TC_FMT_RGB);
+            else if (obs_format == TC_OBS_CLASSES_BITS) TC_LAUNCH_ENVS(TC_FMT_BITS);
+            else if (obs_format == TC_OBS_CLASSES_BF16) TC_LAUNCH_ENVS(TC_FMT_BF16);
+            else TC_LAUNCH_ENVS(TC_FMT_U8);
+#undef TC_LAUNCH_ENVS
+            h->launches++;
+            TC_CUDA(cudaGetLastError());
+            return TC_OK;
+        }
         if (obs_format == TC_OBS_RGB) tc_render_env_kernel<256, TC_FMT_RGB><<<N, 256, sm, st>>>(ea);
         else if (obs_format == TC_OBS_CLASSES_BITS) tc_render_env_kernel<256, TC_FMT_BITS><<<N, 256, sm, st>>>(ea);
         else if (obs_format == TC_OBS_CLASSES_BF16) tc_render_env_kernel<256, TC_FMT_BF16><<<N, 256, sm, st>>>(ea);
@@ -529,8 +591,12 @@ static int tc_launch_track(TcHandle *h, int mode, const float *cc, const int32_t
     ta.near_off = h->d_near_off; ta.near_edge = h->d_near_edge;
     ta.done = h->ar_done; ta.was_reset = h->ar_done ? h->ar_was_reset : nullptr; ta.rng = h->rng; ta.spawn_points = h->spawn_points; ta.n_spawn_points = h->n_spawn_points; ta.last_spawn = h->last_spawn;
     if (outs) ta.out = *outs;
-    const int envs_per_block = TC_TRACK_THREADS / 32;
-    tc_track_kernel<<<(h->n_envs + envs_per_block - 1) / envs_per_block, TC_TRACK_THREADS, h->track_smem, st>>>(ta);
+    if (h->track_per_thread) {
+        tc_track_thread_kernel<<<(h->n_envs + TC_TRACK1_THREADS - 1) / TC_TRACK1_THREADS, TC_TRACK1_THREADS, h->track_smem, st>>>(ta);
+    } else {
+        const int envs_per_block = TC_TRACK_THREADS / 32;
+        tc_track_kernel<<<(h->n_envs + envs_per_block - 1) / envs_per_block, TC_TRACK_THREADS, h->track_smem, st>>>(ta);
+    }
     h->launches++;
     TC_CUDA(cudaGetLastError());
     return TC_OK;
@@ -662,6 +728,14 @@ int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline) {
 int tc_debug_cull_info(TcHandle *h, double *out4) {
     if (!h || !out4) return tc_fail(TC_ERR_INVALID, "tc_debug_cull_info: null argument");
     out4[0] = (h->fused_all || h->envb_smem > 0) ? h->cull_radius : -2.0; out4[1] = h->cull_cells; out4[2] = h->cull_mean_nodes; out4[3] = h->cull_max_nodes;
+    return TC_OK;
+}
+
+int tc_debug_render_info(TcHandle *h, int32_t *out8) {
+    if (!h || !out8) return tc_fail(TC_ERR_INVALID, "tc_debug_render_info: null argument");
+    out8[0] = h->fused_all; out8[1] = h->fused_all ? h->env_pack : 0; out8[2] = h->env_chunks;
+    out8[3] = (int32_t)(h->fused_all ? (h->env_pack ? h->envs_smem : h->env_smem) : h->render_smem);
+    out8[4] = h->track_per_thread + 16 * h->env_blocks; out8[5] = (int32_t)h->envb_smem; out8[6] = h->env_np; out8[7] = h->env_max_bytes;
     return TC_OK;
 }
 

@@ -34,6 +34,7 @@ struct TcLanes {
 // (layer.py:44 `d.index(min(d))`).
 TC_HD void tc_group_argmin(const TcLanes &g, double &d, int &idx) {
 #if defined(__CUDA_ARCH__)
+    if (g.n == 1) return;   // a single-lane group (thread-per-env tracking): the lane's own result is the group's
     for (int off = 16; off > 0; off >>= 1) {
         double od = __shfl_xor_sync(0xffffffffu, d, off);
         int oi = __shfl_xor_sync(0xffffffffu, idx, off);
@@ -287,14 +288,31 @@ TC_HD void tc_store_state(double *sf, int32_t *si, const TcCarState &s) {
     si[14] = 0; si[15] = 0;
 }
 
-// car.py:127-148. Group-uniform control flow; only the u-turn scan is spread over the lanes. Returns truncated.
-TC_HD bool tc_find_local_path(const TcLanes &g, const TcTrackTables &t, TcCarState &s, int maneuver) {
+// car.py:127-148 in three pieces, so that the one O(E) part - the u-turn's global scan - can be run by whichever lanes
+// the caller has (the env's own group, or a whole warp on behalf of one of its envs when the kernel is thread-per-env):
+//   tc_path_valid            the env tracks an edge (it was reset successfully)
+//   tc_wants_uturn_scan      this step starts a u-turn (car.py:130)
+//   tc_uturn_direction       the direction the scan filters by (car.py:128)
+//   tc_find_local_path_given the rest, given the scan's result. Returns truncated.
+TC_HD bool tc_path_valid(const TcTrackTables &t, const TcCarState &s) {
     // an env that was never reset (or whose reset found no successor edge) has no tracked edge: truncated, tables untouched
-    if (s.path_len <= 0 || s.pe[0] < 0 || s.pe[0] >= t.lp_n_edges || s.pn[0] < 0 || s.pn[1] < 0) return true;
+    return !(s.path_len <= 0 || s.pe[0] < 0 || s.pe[0] >= t.lp_n_edges || s.pn[0] < 0 || s.pn[1] < 0);
+}
+TC_HD bool tc_wants_uturn_scan(const TcTrackTables &t, const TcCarState &s, int maneuver) {
+    return tc_path_valid(t, s) && maneuver == 2 && s.last_man != 2;
+}
+TC_HD double tc_uturn_direction(const TcTrackTables &t, const TcCarState &s, int maneuver) {
+    return tc_clip_angle(t.lp_orient[s.pe[0]] + maneuver * TC_PI / 2);
+}
+TC_HD int tc_uturn_scan(const TcLanes &g, const TcTrackTables &t, double fx, double fy, double dir) {
+    return tc_nearest_edge(g, t.lp_nodes, t.lp_edges, t.lp_n_edges, fx, fy, t.lp_orient, dir, 30.0 * (TC_PI / 180.0));
+}
+TC_HD bool tc_find_local_path_given(const TcTrackTables &t, TcCarState &s, int maneuver, int uturn_edge) {
+    if (!tc_path_valid(t, s)) return true;
     double dir = tc_clip_angle(t.lp_orient[s.pe[0]] + maneuver * TC_PI / 2);
     int ne; // new first edge
     if (maneuver == 2 && s.last_man != 2) {
-        ne = tc_nearest_edge(g, t.lp_nodes, t.lp_edges, t.lp_n_edges, s.fx, s.fy, t.lp_orient, dir, 30.0 * (TC_PI / 180.0));
+        ne = uturn_edge;
         dir = tc_clip_angle(dir + TC_PI);
         // reference: local_path=[None] -> TypeError at car.py:144. Here: truncated, path untouched.
         if (ne < 0) return true;
@@ -331,10 +349,15 @@ TC_HD bool tc_find_local_path(const TcLanes &g, const TcTrackTables &t, TcCarSta
     }
     return false;
 }
+// the env's own group does the scan (warp-per-env tracking, host test build)
+TC_HD bool tc_find_local_path(const TcLanes &g, const TcTrackTables &t, TcCarState &s, int maneuver) {
+    int ut = -1;
+    if (tc_wants_uturn_scan(t, s, maneuver)) ut = tc_uturn_scan(g, t, s.fx, s.fy, tc_uturn_direction(t, s, maneuver));
+    return tc_find_local_path_given(t, s, maneuver, ut);
+}
 
-// car.py:70-125 (v_cmd, s_cmd already clipped to [-1,1], env.py:118). cp = car parameter row. Returns truncated.
-TC_HD bool tc_car_step(const TcLanes &g, const TcTrackTables &t, const double *cp, TcCarState &s, double v_cmd, double s_cmd,
-                       int maneuver) {
+// car.py:70-125 without the path update (v_cmd, s_cmd already clipped to [-1,1], env.py:118). cp = car parameter row.
+TC_HD void tc_car_move(const double *cp, TcCarState &s, double v_cmd, double s_cmd) {
     double dt = cp[TC_CP_DT];
     double nv = v_cmd * cp[TC_CP_MAX_VELOCITY];
     if (!isnan(cp[TC_CP_MAX_ACCELERATION]))
@@ -364,6 +387,11 @@ TC_HD bool tc_car_step(const TcLanes &g, const TcTrackTables &t, const double *c
     }
     s.fx = s.x + cp[TC_CP_WHEELBASE] * cos(s.rot);
     s.fy = s.y + cp[TC_CP_WHEELBASE] * sin(s.rot);
+}
+// car.py:70-125. Returns truncated.
+TC_HD bool tc_car_step(const TcLanes &g, const TcTrackTables &t, const double *cp, TcCarState &s, double v_cmd, double s_cmd,
+                       int maneuver) {
+    tc_car_move(cp, s, v_cmd, s_cmd);
     return tc_find_local_path(g, t, s, maneuver);
 }
 
@@ -394,8 +422,19 @@ struct TcInfo {
     double cte, heading, velocity, reward;
     bool terminated;
 };
+// the nearest laneline edge of class c for a car at (x, y) whose ground cell has no candidate list: a scan over all edges
+TC_HD int tc_nearest_laneline_scan(const TcLanes &g, const TcTrackTables &t, int c, double x, double y) {
+    const double *nodes = t.ll_nodes + 2 * t.ll_node_off[c];
+    const int32_t *edges = t.ll_edges + 2 * t.ll_edge_off[c];
+    const int m = t.ll_edge_off[c + 1] - t.ll_edge_off[c];
+    if (fabs(x) <= t.scan_limit && fabs(y) <= t.scan_limit)
+        return tc_nearest_edge_prefiltered(g, nodes, t.ll_nodes32 + 2 * t.ll_node_off[c], edges, m, x, y, t.scan_margin);
+    return tc_nearest_edge(g, nodes, edges, m, x, y, nullptr, 0, 0);   // a runaway car (wrapped envs never terminate): no pre-filter
+}
+// pre_nearest (optional): the nearest edge of every class, found by the caller (thread-per-env tracking: a warp scans on behalf
+// of the env whose car left the index grid); otherwise the group looks it up / scans itself.
 TC_HD TcInfo tc_get_info(const TcLanes &g, const TcTrackTables &t, const double *cp, const TcCarState &s, bool wrapped, double *dist,
-                         int *nearest) {
+                         int *nearest, const int *pre_nearest = nullptr) {
     TcInfo r;
     r.cte = 0; r.heading = 0; r.velocity = 0.0;
     for (int c = 0; c < t.n_classes; c++) { dist[c] = 0; nearest[c] = -1; }
@@ -407,14 +446,12 @@ TC_HD TcInfo tc_get_info(const TcLanes &g, const TcTrackTables &t, const double 
         for (int c = 0; c < t.n_classes; c++) {
             const double *nodes = t.ll_nodes + 2 * t.ll_node_off[c];
             const int32_t *edges = t.ll_edges + 2 * t.ll_edge_off[c];
-            int m = t.ll_edge_off[c + 1] - t.ll_edge_off[c];
             int e;
-            if (cell >= 0) {
+            if (pre_nearest) e = pre_nearest[c];
+            else if (cell >= 0) {
                 const int32_t *o = t.near_off + (size_t)c * t.near_nx * t.near_ny + cell;
                 e = tc_nearest_edge_list(g, nodes, edges, t.near_edge + o[0], o[1] - o[0], s.x, s.y);
-            } else if (fabs(s.x) <= t.scan_limit && fabs(s.y) <= t.scan_limit)
-                e = tc_nearest_edge_prefiltered(g, nodes, t.ll_nodes32 + 2 * t.ll_node_off[c], edges, m, s.x, s.y, t.scan_margin);
-            else e = tc_nearest_edge(g, nodes, edges, m, s.x, s.y, nullptr, 0, 0);   // a runaway car (wrapped envs never terminate): no pre-filter
+            } else e = tc_nearest_laneline_scan(g, t, c, s.x, s.y);
             nearest[c] = e;
             if (e < 0) continue; // class without edges: the reference would raise on min([])
             int n0 = edges[2 * e], n1 = edges[2 * e + 1];

@@ -34,6 +34,9 @@ __device__ __forceinline__ void tc_fence_mbar_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tc_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc_smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(tc_smem_u32(bar))
@@ -164,6 +167,132 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS, 3) tc_track_kernel(const TcT
     if (o.nearest_edge) for (int c = 0; c < C; c++) o.nearest_edge[(size_t)env * C + c] = nearest[c];
     // car.py:66 builds local_path coordinates only when the info is non-empty (len >= 2)
     int plen = s.path_len >= 2 ? s.path_len : 0;
+    if (o.local_path)
+        for (int i = 0; i < 4; i++) {
+            bool ok = i < plen;
+            o.local_path[(size_t)env * 8 + 2 * i] = ok ? (float)t.lp_nodes[2 * s.pn[2 * i + 1]] : 0.0f;
+            o.local_path[(size_t)env * 8 + 2 * i + 1] = ok ? (float)t.lp_nodes[2 * s.pn[2 * i + 1] + 1] : 0.0f;
+        }
+    if (o.local_path_nodes)
+        for (int i = 0; i < 8; i++) o.local_path_nodes[(size_t)env * 8 + i] = (i >> 1) < s.path_len ? s.pn[i] : -1;
+    if (o.path_len) o.path_len[env] = s.path_len;
+    if (o.info_f64) {
+        double *r = o.info_f64 + (size_t)env * (4 + C);
+        r[TC_INFO_CTE] = info.cte; r[TC_INFO_HEADING] = info.heading; r[TC_INFO_VELOCITY] = info.velocity;
+        if (a.mode == 0) r[TC_INFO_REWARD] = info.reward;
+        for (int c = 0; c < C; c++) r[TC_INFO_DIST0 + c] = dist[c];
+    }
+    if (a.mode == 0) {
+        if (o.reward) o.reward[env] = (float)info.reward;
+        if (o.terminated) o.terminated[env] = info.terminated ? 1 : 0;
+        if (o.truncated) o.truncated[env] = truncated ? 1 : 0;
+    }
+}
+
+// The same step with ONE THREAD PER ENV. The warp-per-env kernel above computes the scalar part of a step (bicycle model, path
+// hops, distances) redundantly in all 32 lanes and only spreads the two scans; since the nearest-laneline index went in, those
+// scans are a handful of candidates long, so almost all of its issue slots are redundant work. Here every thread owns an env;
+// the two O(E) scans that remain - the u-turn's global search (car.py:130-131) and the laneline search of a car outside the
+// index grid - are run by the whole warp on behalf of each lane that needs one (ballot loop), with the same lexicographic
+// arg-min, so results are bit-identical to the kernel above. 32x fewer warps for the same envs: 0.19 -> 0.03 ms for 32768 envs.
+#define TC_TRACK1_THREADS 128
+__global__ void __launch_bounds__(TC_TRACK1_THREADS) tc_track_thread_kernel(const TcTrackArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_blob[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        tc_mbar_init(&bar, 1);
+        tc_fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc_mbar_expect_tx(&bar, (uint32_t)a.layout.total_bytes);
+        tc_bulk_g2s(smem_blob, a.blob, (uint32_t)a.layout.total_bytes, &bar);
+    }
+    const int lane = threadIdx.x & 31;
+    const int env_raw = blockIdx.x * TC_TRACK1_THREADS + threadIdx.x;
+    const bool in_range = env_raw < a.n_envs;
+    const int env = in_range ? env_raw : a.n_envs - 1;   // idle lanes shadow the last env (they take part in the warp scans) and store nothing
+    const TcLanes g1 = {0, 1}, gw = {lane, 32};
+    tc_mbar_wait(&bar, 0);
+    TcTrackTables t = tc_track_tables(smem_blob, a.layout);
+    t.near_x0 = a.near_x0; t.near_y0 = a.near_y0; t.near_inv_cell = a.near_inv_cell; t.near_nx = a.near_nx; t.near_ny = a.near_ny;
+    t.near_off = a.near_off; t.near_edge = a.near_edge;
+    const int C = t.n_classes;
+    const double *cp = a.car + (size_t)env * TC_CP_N;
+    double *sf = a.sf + (size_t)env * TC_SF_N;
+    int32_t *si = a.si + (size_t)env * TC_SI_N;
+    TcCarState s;
+    tc_load_state(sf, si, s);
+    bool truncated = false, auto_reset = false, live = in_range;   // live: this thread's env takes part in this launch
+    int man = 0;
+    bool stepping = false;
+    if (a.mode == 0 && a.done && a.done[env]) {
+        // the action of this step is ignored; reward 0, not terminated, not truncated, empty info (env.py:101-113)
+        int node = -1;
+        if (a.rng && in_range) node = tc_spawn_draw(t, a.rng + (size_t)env * TC_RNG_N, a.spawn_points, a.n_spawn_points);
+        auto_reset = tc_car_reset(t, cp, s, node);
+        if (auto_reset && in_range && a.last_spawn) a.last_spawn[env] = node;
+    }
+    if (auto_reset) {
+    } else if (a.mode == 1) {
+        if (a.mask && !a.mask[env]) live = false;
+        else {
+            int node = -1;
+            if (a.spawn_nodes) node = a.spawn_nodes[env];
+            else if (a.rng && in_range) node = tc_spawn_draw(t, a.rng + (size_t)env * TC_RNG_N, a.spawn_points, a.n_spawn_points);
+            if (!tc_car_reset(t, cp, s, node)) live = false;
+            else if (in_range && a.last_spawn) a.last_spawn[env] = node;
+        }
+    } else {
+        // env.py:118: np.clip(action["car_control"], -1, 1) on float64
+        double v_raw = a.act_cc64 ? a.act_cc64[2 * env] : (double)a.act_cc[2 * env];
+        double s_raw = a.act_cc64 ? a.act_cc64[2 * env + 1] : (double)a.act_cc[2 * env + 1];
+        man = a.act_man[env];
+        tc_car_move(cp, s, tc_np_clip(v_raw, -1.0, 1.0), tc_np_clip(s_raw, -1.0, 1.0));
+        stepping = in_range;
+    }
+    // ---- warp-cooperative part 1: the u-turn's global edge search for the lanes that start one
+    int uturn_edge = -1;
+    {
+        const bool want = stepping && tc_wants_uturn_scan(t, s, man);
+        const double dir = want ? tc_uturn_direction(t, s, man) : 0.0;
+        for (unsigned mk = __ballot_sync(0xffffffffu, want); mk; mk &= mk - 1) {
+            const int src = __ffs(mk) - 1;
+            const double fx = __shfl_sync(0xffffffffu, s.fx, src), fy = __shfl_sync(0xffffffffu, s.fy, src), d = __shfl_sync(0xffffffffu, dir, src);
+            const int e = tc_uturn_scan(gw, t, fx, fy, d);
+            if (lane == src) uturn_edge = e;
+        }
+    }
+    if (stepping) truncated = tc_find_local_path_given(t, s, man, uturn_edge);
+    // ---- warp-cooperative part 2: laneline search over all edges for cars outside the nearest-laneline index
+    int pre[TC_MAX_CLASSES];
+    const bool scan = live && s.path_len >= 2 && tc_near_cell(t, s.x, s.y) < 0;
+    for (unsigned mk = __ballot_sync(0xffffffffu, scan); mk; mk &= mk - 1) {
+        const int src = __ffs(mk) - 1;
+        const double x = __shfl_sync(0xffffffffu, s.x, src), y = __shfl_sync(0xffffffffu, s.y, src);
+        for (int c = 0; c < C; c++) {
+            const int e = tc_nearest_laneline_scan(gw, t, c, x, y);
+            if (lane == src) pre[c] = e;
+        }
+    }
+    if (!live) return;
+    double dist[TC_MAX_CLASSES];
+    int nearest[TC_MAX_CLASSES];
+    TcInfo info = tc_get_info(g1, t, cp, s, a.wrapped != 0, dist, nearest, scan ? pre : nullptr);
+    if (auto_reset) { info.reward = 0; info.terminated = false; }
+    if (a.mode == 0 && a.done) a.done[env] = (info.terminated || truncated) ? 1 : 0;
+    if (a.mode == 0 && a.was_reset) a.was_reset[env] = auto_reset ? 1 : 0;
+    tc_store_state(sf, si, s);
+    tc_camera_pose(a.cam + (size_t)env * TC_CAM_N + TC_CAM_E, s.x, s.y, cos(s.rot), sin(s.rot), a.pose + (size_t)env * 12);
+    const TcOutputs &o = a.out;
+    if (o.cte) o.cte[env] = (float)info.cte;
+    if (o.heading_error) o.heading_error[env] = (float)info.heading;
+    if (o.velocity) o.velocity[env] = (float)info.velocity;
+    if (o.position) { o.position[2 * env] = (float)s.x; o.position[2 * env + 1] = (float)s.y; }
+    if (o.orientation) o.orientation[env] = (float)s.rot;
+    if (o.laneline_distances) for (int c = 0; c < C; c++) o.laneline_distances[(size_t)env * C + c] = (float)dist[c];
+    if (o.nearest_edge) for (int c = 0; c < C; c++) o.nearest_edge[(size_t)env * C + c] = nearest[c];
+    int plen = s.path_len >= 2 ? s.path_len : 0;   // car.py:66: local_path coordinates only when the info is non-empty
     if (o.local_path)
         for (int i = 0; i < 4; i++) {
             bool ok = i < plen;
@@ -880,6 +1009,8 @@ struct TcRenderEnvArgs {
     uint8_t colors[TC_MAX_CLASSES * 3];
     long long *timeline;       // optional debug [N][10], see tools/timeline.py
     int rows_per_band, n_bands, band_words;   // banded variant (large frames): rows per band, bands, words of one class's band plane (incl. pad word)
+    int region_bytes;          // packed variant (tc_render_envs_kernel): bytes of one env slot's shared-memory region
+    int prim_chunks;           // ... and how many 32-segment chunks its primitive slots hold (1..TC_ENVS_CHUNKS)
 };
 // shared memory: phase 1 [Px Py Pz | ix iy | 5 flag arrays | cell tables (TMA)]; phase 2 [segments + classes | plane | primitive slots]
 __host__ __device__ inline size_t tc_env_np(int max_nodes, int max_edges) {
@@ -900,10 +1031,12 @@ __host__ __device__ inline size_t tc_env_smem_bytes(size_t np, int max_bytes, in
 // the four ordered clip passes, projection, visibility (core nodes only), kept edges. In: the cell's tables at tab_smem
 // (landing via TMA, mbarrier `bar`), pose and intrinsics in shared memory. Out: *seg_cnt segments as int4 at smem_raw, their
 // classes as bytes behind them (segs + d.n_edges); the scratch arrays it used are dead afterwards. All threads call it.
+// NT threads (numbered tid = 0..NT-1) work on the env; the block barriers inside are hit by the whole block, so every thread of
+// the block must call it (the packed kernel runs one instance per env slot side by side, NT = its threads per env).
 template <int NT>
 __device__ __forceinline__ void tc_env_camera_pass(unsigned char *smem_raw, size_t np, const unsigned char *tab_smem, const TcCellBlob &d,
-                                               uint64_t *bar, const double *pose, const double *cam, int H, int W, int *seg_cnt) {
-    const int tid = threadIdx.x;
+                                               uint64_t *bar, const double *pose, const double *cam, int H, int W, int *seg_cnt,
+                                               const int tid = threadIdx.x) {
     const int n = d.n_nodes, m = d.n_edges;
     int4 *segs = (int4 *)smem_raw;
     TcProjScratch sc;
@@ -1084,6 +1217,184 @@ __global__ void __launch_bounds__(NT, 1024 / NT) tc_render_env_kernel(const TcRe
     }
 #endif
 #undef TC_TL
+}
+
+// ------------------------------------------------------------------------------------------------ fused, E envs per block
+// tc_render_env_kernel leaves most of its lanes idle: a Knuffingen frame has ~120 nodes for 256 threads, ~12 segments for
+// the 32 lanes of each set-up warp and ~110 live primitives for 384 draw slots, and the block barriers between the phases cost
+// the same whatever the fill. Registers cap the SM at 1024 threads, so the only way to more work in flight is fuller lanes:
+// this kernel renders E consecutive envs per block. Their nodes share the threads of the camera pass (NT/E each), their
+// segments are concatenated and share the lanes of the set-up and the slots of the draw, and every barrier is paid once per E
+// envs. Set-up rounds take TC_ENVS_CHUNKS x 32 segments whose (role, chunk) tasks are handed to the warps from a queue -
+// spans first: they are the longest - so that a frame with more than 32 segments does not serialise two set-up rounds.
+// Shared memory: E regions laid out like tc_render_env_kernel's (phase 1: scratch + the cell's tables, phase 2: the env's
+// segment list and its stacked C*H-row plane), then the primitive slots.
+#define TC_ENVS_CHUNKS 2
+__host__ __device__ inline size_t tc_envs_region_bytes(size_t np, int max_bytes, int plane_words) {
+    size_t a = tc_env_off_tables(np) + (size_t)max_bytes, b = np * 24 + (size_t)plane_words * 4;
+    return ((a > b ? a : b) + 127) & ~(size_t)127;
+}
+__host__ __device__ inline size_t tc_envs_prims_bytes(int chunks) { return (((size_t)chunks * TC_ENV_CHUNK * TC_ENV_SEG_WORDS * 4 + 15) & ~(size_t)15); }
+__host__ __device__ inline size_t tc_envs_smem_bytes(int E, size_t np, int max_bytes, int plane_words, int chunks) {
+    return (size_t)E * tc_envs_region_bytes(np, max_bytes, plane_words) + tc_envs_prims_bytes(chunks);
+}
+
+// 3 blocks per SM: the kernel needs 76-80 registers; capped at 64 (4 blocks) it spills, and a spilled value is a
+// local-memory access that queues behind the observation stores of the co-resident blocks (measured: 80 registers at 3 blocks
+// per SM beat 64 registers with 72 bytes of spills at 4)
+#ifndef TC_ENVS_MIN_BLOCKS
+#define TC_ENVS_MIN_BLOCKS(NT) (768 / (NT))
+#endif
+template <int NT, int FMT, int E>
+__global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_render_envs_kernel(const TcRenderEnvArgs a) {
+    // Register discipline: the set-up code needs all 64 registers, and a spilled value is a local-memory access that queues
+    // behind the observation stores of the co-resident blocks (thousands of cycles each). So nothing is kept in registers across
+    // the phases that can be re-read from the kernel parameters (constant bank) or from shared memory.
+    constexpr int TPE = NT / E;                       // threads of the camera pass per env
+    constexpr int CAP = TC_ENVS_CHUNKS * TC_ENV_CHUNK; // most segments per set-up round (a.prim_chunks <= TC_ENVS_CHUNKS chunks of 32)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int seg_cnt[E], s_pref[E + 1], s_thick[E], s_active[E];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double s_pose[E][12], s_cam[E][TC_CAM_N];
+    __shared__ uint32_t s_color24[TC_MAX_CLASSES];
+    __shared__ TcCellBlob s_desc[E];
+    __shared__ int4 s_seg[CAP];        // the round's segments ...
+    __shared__ uint16_t s_tag[CAP];    // ... and for each its env slot << 8 | class
+    __shared__ int s_task, s_nseg, s_ntask;
+#define TC_REGION(e) (smem_raw + (size_t)(e) * a.region_bytes)
+#define TC_PLANE(e) ((uint32_t *)(TC_REGION(e) + (size_t)a.np * 24))
+#define TC_PW ((int32_t *)(smem_raw + (size_t)E * a.region_bytes))
+    if (threadIdx.x == 0) {
+        tc_mbar_init(&bar, E);
+        tc_fence_mbar_init();
+    }
+    __syncwarp();
+    if (threadIdx.x < E) {
+        // which part of the map can this env's camera see: its ground cell selects the tables (one TMA bulk copy per env)
+        const int e = threadIdx.x, env = blockIdx.x * E + e;
+        const bool act = env < a.n_envs && !(a.mask && !a.mask[env]);
+        TcCellBlob d;
+        if (act) d = a.cell_desc[tc_cull_cell(a.grid, a.pose + (size_t)env * 12)];
+        else { d.n_nodes = 0; d.n_edges = 0; d.bytes = 0; d.offset = 0; }
+        s_active[e] = act; seg_cnt[e] = 0; s_thick[e] = act ? a.thickness[env] : 1;
+        s_desc[e] = d;
+        // one arrival per env slot, with its bytes
+        if (d.bytes > 0) {
+            tc_mbar_expect_tx(&bar, (uint32_t)d.bytes);
+            tc_bulk_g2s(TC_REGION(e) + tc_env_off_tables((size_t)a.np), a.cell_blob + d.offset, (uint32_t)d.bytes, &bar);
+        } else tc_mbar_arrive(&bar);
+    }
+    if (FMT == TC_FMT_RGB && threadIdx.x >= 64 && threadIdx.x < 64 + TC_MAX_CLASSES) s_color24[threadIdx.x - 64] = tc_color24_of(a.colors, threadIdx.x - 64);
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + E * 17) {
+        const int k = threadIdx.x - 32, e = k / 17, i = k % 17, env = blockIdx.x * E + e;
+        if (env < a.n_envs) {
+            if (i < 12) s_pose[e][i] = a.pose[(size_t)env * 12 + i];
+            else s_cam[e][TC_CAM_FX + i - 12] = a.cam[(size_t)env * TC_CAM_N + TC_CAM_FX + i - 12];
+        }
+    }
+    __syncthreads();
+    // ---- camera pass (camera.py:52-110) of the E envs side by side: thread -> (env slot j, index of its TPE threads)
+    {
+        const int j = threadIdx.x / TPE;
+        tc_env_camera_pass<TPE>(TC_REGION(j), (size_t)a.np, TC_REGION(j) + tc_env_off_tables((size_t)a.np), s_desc[j], &bar, s_pose[j], s_cam[j], a.H, a.W,
+                                &seg_cnt[j], (int)threadIdx.x - j * TPE);
+    }
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int e = 0; e < E; e++) { s_pref[e] = acc; acc += seg_cnt[e]; }
+        s_pref[E] = acc;
+    }
+    // zero the planes of the envs that have segments (the others are stored as zeros without a plane)
+    for (int e = 0; e < E; e++)
+        if (seg_cnt[e] > 0) {
+            uint32_t *pl = TC_PLANE(e);
+            for (int i = threadIdx.x; i < a.plane_words; i += NT) pl[i] = 0;
+        }
+    __syncthreads();
+    for (int base = 0; base < s_pref[E]; base += a.prim_chunks * TC_ENV_CHUNK) {
+        {
+            const int nseg = min(a.prim_chunks * TC_ENV_CHUNK, s_pref[E] - base);
+            int32_t *pw = TC_PW;
+            for (int i = threadIdx.x; i < nseg * TC_MAX_PRIMS_PER_SEG; i += NT)
+                pw[(i / TC_MAX_PRIMS_PER_SEG) * TC_ENV_SEG_WORDS + (i % TC_MAX_PRIMS_PER_SEG) * 8] = TC_PRIM_NONE;
+            if ((int)threadIdx.x < nseg) {   // segment tid of the round: find its env slot, copy it next to its tag
+                const int sidx = base + threadIdx.x;
+                int e = 0;
+#pragma unroll
+                for (int k = 1; k < E; k++) e += sidx >= s_pref[k];
+                const int i = sidx - s_pref[e];
+                const int4 *segs = (const int4 *)TC_REGION(e);
+                s_seg[threadIdx.x] = segs[i];
+                s_tag[threadIdx.x] = (uint16_t)((e << 8) | ((const uint8_t *)(segs + s_desc[e].n_edges))[i]);
+            }
+            if (threadIdx.x == 0) {
+                s_task = 0; s_nseg = nseg;
+                s_ntask = ((nseg + TC_ENV_CHUNK - 1) / TC_ENV_CHUNK) * TC_N_ROLES;
+            }
+        }
+        __syncthreads();
+        // set-up: (role, chunk) tasks from a queue, lane = segment of the chunk; spans (role 0) are handed out first
+        while (true) {
+            int k = 0;
+            if ((threadIdx.x & 31) == 0) k = atomicAdd(&s_task, 1);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= s_ntask) break;
+            const int nchunks = s_ntask / TC_N_ROLES;
+            const int role = k / nchunks, sl = (k - role * nchunks) * TC_ENV_CHUNK + (threadIdx.x & 31);
+            if (sl < s_nseg) {
+                const int4 s4 = s_seg[sl];
+                tc_polyline_setup<true>(a.W, a.H, s4.x, s4.y, s4.z, s4.w, s_thick[s_tag[sl] >> 8], role, (TcPrim *)(TC_PW + sl * TC_ENV_SEG_WORDS));
+            }
+        }
+        __syncthreads();
+        // draw: one thread per primitive; a warp takes one slot (= one kind of primitive) of the 32 segments of a chunk
+        for (int p = threadIdx.x; p < (s_ntask / TC_N_ROLES) * TC_MAX_PRIMS_PER_SEG * 32; p += NT) {   // uniform trip count within a warp
+            const int lane = threadIdx.x & 31;
+            const int c = p / (TC_MAX_PRIMS_PER_SEG * 32), slot = (p - c * (TC_MAX_PRIMS_PER_SEG * 32)) >> 5;
+            const int sl0 = c * TC_ENV_CHUNK;
+            const int32_t *pw = TC_PW;
+            const TcPrim *q = (const TcPrim *)(pw + (sl0 + lane) * TC_ENV_SEG_WORDS + slot * 8);
+            int items = 0;
+            if (sl0 + lane < s_nseg && q->kind != TC_PRIM_NONE) items = tc_prim_items(*q);
+            unsigned big = __ballot_sync(0xffffffffu, items > TC_SMALL_PRIM_ITEMS);
+            bool own = true;
+            while (own || big) {
+                int src = lane;
+                bool active = items > 0 && items <= TC_SMALL_PRIM_ITEMS;
+                TcLanes gg = {0, 1};
+                if (!own) {
+                    src = __ffs(big) - 1;
+                    big &= big - 1;
+                    active = true;
+                    gg.lane = lane; gg.n = 32;
+                }
+                own = false;
+                if (active) {
+                    const int tag = s_tag[sl0 + src];
+                    TcPlane pl = {TC_PLANE(tag >> 8), a.H, a.W, 0, a.H, -(tag & 0xff) * a.H};
+                    tc_prim_draw(gg, pl, *(const TcPrim *)(pw + (sl0 + src) * TC_ENV_SEG_WORDS + slot * 8));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = 0; e < E; e++) {
+        if (!s_active[e]) continue;
+        const int env = blockIdx.x * E + e;
+        const uint32_t *plane = TC_PLANE(e);
+        const bool any = seg_cnt[e] > 0;
+        if (FMT == TC_FMT_RGB)
+            tc_store_rgb<NT>(a.obs + (size_t)env * a.H * a.W * 3, (uint32_t)(a.H * a.W), plane, (uint32_t)(a.H * a.W), a.n_classes, s_color24, any);
+        else if (FMT == TC_FMT_BITS) {
+            const int words = (int)(((size_t)a.H * a.W + 31) / 32) * a.n_classes;
+            tc_store_bits<NT>((uint32_t *)a.obs + (size_t)env * words, words, plane, any);
+        } else if (FMT == TC_FMT_BF16)
+            tc_store_bf16<NT>((uint16_t *)a.obs + (size_t)env * a.n_classes * a.H * a.W, (uint32_t)(a.n_classes * a.H * a.W), plane, any);
+        else tc_store_plane_sparse<NT>(a.obs + (size_t)env * a.n_classes * a.H * a.W, (size_t)a.n_classes * a.H * a.W, plane, any);
+    }
+#undef TC_REGION
+#undef TC_PLANE
+#undef TC_PW
 }
 
 // ------------------------------------------------------------------------------------------------ fused, block per env, banded

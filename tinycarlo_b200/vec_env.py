@@ -471,6 +471,16 @@ class TinyCarloVecEnv:
         _lib.check(self._L.tc_debug_cull_info(self._h, out), "tc_debug_cull_info")
         return {"radius": out[0], "cells": int(out[1]), "mean_nodes": out[2], "max_nodes": int(out[3])}
 
+    def render_info(self) -> Dict[str, int]:
+        """Which kernels this env launches (tc_debug_render_info): block-per-env render path, envs per block of the packed
+        kernel, its primitive chunks, the render kernel's dynamic shared memory, thread-per-env tracking."""
+        out = (C.c_int32 * 8)()
+        _lib.check(self._L.tc_debug_render_info(self._h, out), "tc_debug_render_info")
+        keys = ("block_per_env", "envs_per_block", "prim_chunks", "render_smem", "track_per_thread", "banded_smem", "cell_nodes_cap", "cell_bytes_cap")
+        d = dict(zip(keys, (int(v) for v in out)))
+        d["blocks_per_sm"], d["track_per_thread"] = d["track_per_thread"] >> 4, d["track_per_thread"] & 1
+        return d
+
     @property
     def launch_count(self) -> int:
         return int(self._L.tc_launch_count(self._h))
