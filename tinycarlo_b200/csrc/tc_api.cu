@@ -85,6 +85,9 @@ struct TcHandle {
     TcCullGrid cull_grid{};
     int env_np = 0, env_max_bytes = 0, env_words = 0;
     size_t env_smem = 0;     // tc_render_env_kernel (small frames)
+    // two-kernel path of large bit-packed frames (tc_prims_kernel + tc_draw_class_kernel): buffers allocated at first use
+    TcPrimsOut prims{};
+    int prims_on = 1;
     int env_blocks = 0;      // resident blocks per SM of the packed kernel as chosen (diagnostics)
     int env_pack = 0, env_chunks = 1;   // > 0: tc_render_envs_kernel with that many envs per block
     size_t envs_smem = 0;
@@ -374,6 +377,9 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     TC_CUDAH(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
     TC_PREP_RENDER((tc_render_env_banded_kernel<TC_FMT_RGB>));
     TC_PREP_RENDER((tc_render_env_banded_kernel<TC_FMT_BITS>));
+    TC_PREP_RENDER((tc_prims_kernel<256, 2>));
+    TC_PREP_RENDER((tc_draw_class_kernel<256, TC_FMT_BITS>));
+    if (const char *po = getenv("TC_PRIMS_PATH")) h->prims_on = atoi(po) != 0;
     if (h->fused_ok) {
         if (const char *rt = getenv("TC_RENDER_THREADS")) h->render_threads = atoi(rt) == 128 ? 128 : 256;
         TC_PREP_RENDER((tc_render_env_kernel<128, TC_FMT_U8>));
@@ -513,6 +519,43 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
         else if (obs_format == TC_OBS_CLASSES_BF16) tc_render_env_kernel<256, TC_FMT_BF16><<<N, 256, sm, st>>>(ea);
         else if (h->render_threads == 128) tc_render_env_kernel<128, TC_FMT_U8><<<N, 128, sm, st>>>(ea);
         else tc_render_env_kernel<256, TC_FMT_U8><<<N, 256, sm, st>>>(ea);
+        h->launches++;
+        TC_CUDA(cudaGetLastError());
+        return TC_OK;
+    }
+    if (obs && !h->fused_all && h->envb_on && h->envb_smem > 0 && h->prims_on && !seg_count_out && !seg_out && obs_format == TC_OBS_CLASSES_BITS &&
+        (h->H * h->W) % 128 == 0 && (size_t)h->plane_words_full * 4 <= 64 * 1024) {
+        // large frames, 1 bit per pixel: geometry + set-up once per env (primitives to L2), then a block per (env, class) draws and stores;
+        // envs with more segments than the primitive buffer holds are flagged and rendered by the banded kernel below
+        if (!h->prims.prims) {
+            TC_TRY(tc_dev_alloc(h, &h->prims.prims, (size_t)N * TC_PRIMS_CAP * TC_PRIMS_SEG_WORDS));
+            TC_TRY(tc_dev_alloc(h, &h->prims.tags, (size_t)N * TC_PRIMS_CAP));
+            TC_TRY(tc_dev_alloc(h, &h->prims.count, (size_t)N));
+            TC_TRY(tc_dev_alloc(h, &h->prims.overflow, (size_t)N));
+            TC_CUDA(cudaMemsetAsync(h->prims.count, 0, (size_t)N * 4, st));
+            TC_CUDA(cudaMemsetAsync(h->prims.overflow, 0, (size_t)N, st));
+        }
+        TcRenderEnvArgs ea;
+        ea.cell_desc = h->d_cell_desc; ea.cell_blob = h->d_cell_blob; ea.grid = h->cull_grid; ea.n_envs = N; ea.n_classes = C;
+        ea.np = h->env_np; ea.max_bytes = h->env_max_bytes; ea.H = h->H; ea.W = h->W; ea.plane_words = 0;
+        ea.pose = h->d_pose; ea.cam = h->d_cam; ea.thickness = h->d_thick; ea.mask = mask; ea.obs = nullptr;
+        memcpy(ea.colors, h->colors, sizeof(ea.colors));
+        ea.timeline = nullptr;
+        ea.rows_per_band = h->envb_rows; ea.n_bands = h->envb_bands; ea.band_words = h->envb_words;
+        ea.region_bytes = (int)tc_envs_region_bytes((size_t)h->env_np, h->env_max_bytes, 0);
+        ea.prim_chunks = 1;
+        if (after_project) TC_CUDA(cudaEventRecord(after_project, st));
+        const size_t sm1 = tc_envs_smem_bytes(2, (size_t)h->env_np, h->env_max_bytes, 0, 1);
+        tc_prims_kernel<256, 2><<<(N + 1) / 2, 256, sm1, st>>>(ea, h->prims);
+        h->launches++;
+        TC_CUDA(cudaGetLastError());
+        TcDrawArgs da;
+        da.n_envs = N; da.n_classes = C; da.H = h->H; da.W = h->W; da.plane_words = h->plane_words_full; da.mask = mask; da.in = h->prims; da.obs = obs;
+        tc_draw_class_kernel<256, TC_FMT_BITS><<<N * C, 256, (size_t)h->plane_words_full * 4, st>>>(da);
+        h->launches++;
+        TC_CUDA(cudaGetLastError());
+        ea.mask = h->prims.overflow; ea.obs = obs;   // (the flag is only set for envs the caller's mask selected)
+        tc_render_env_banded_kernel<TC_FMT_BITS><<<std::min(N, 2 * h->n_sms), 256, h->envb_smem, st>>>(ea);   // few blocks scan the (sparse) flags
         h->launches++;
         TC_CUDA(cudaGetLastError());
         return TC_OK;

@@ -1036,7 +1036,7 @@ __host__ __device__ inline size_t tc_env_smem_bytes(size_t np, int max_bytes, in
 template <int NT>
 __device__ __forceinline__ void tc_env_camera_pass(unsigned char *smem_raw, size_t np, const unsigned char *tab_smem, const TcCellBlob &d,
                                                uint64_t *bar, const double *pose, const double *cam, int H, int W, int *seg_cnt,
-                                               const int tid = threadIdx.x) {
+                                               const int tid = threadIdx.x, const uint32_t phase = 0 /* mbarrier parity; 0xffffffff: nothing to wait for */) {
     const int n = d.n_nodes, m = d.n_edges;
     int4 *segs = (int4 *)smem_raw;
     TcProjScratch sc;
@@ -1045,7 +1045,7 @@ __device__ __forceinline__ void tc_env_camera_pass(unsigned char *smem_raw, size
     uint8_t *fA = (uint8_t *)(sc.iy + np), *fB = fA + np, *rA = fB + np, *rB = rA + np;
     sc.vis = rB + np; sc.front = fA; sc.inr = rA;
     const double max_range = cam[TC_CAM_MAX_RANGE];
-    tc_mbar_wait(bar, 0); // the cell's tables have landed in shared memory
+    if (phase != 0xffffffffu) tc_mbar_wait(bar, phase); // the cell's tables have landed in shared memory
     const TcClassTables ct = tc_class_tables_from_cell(tab_smem, d);
     const uint8_t *core = tab_smem + d.off_core, *edge_cls = tab_smem + d.off_edge_cls;
     for (int v = tid; v < n; v += NT) {
@@ -1397,6 +1397,213 @@ __global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_render_envs_ker
 #undef TC_PW
 }
 
+// ------------------------------------------------------------------------------------------------ large frames, 1 bit per pixel: two kernels
+// A 480x640 frame as bit planes is 5 x 38.4 KB: too large for one block to hold all classes, and a block per (env, class) that
+// runs the whole pipeline pays the camera pass and the set-up five times per env (the banded kernel above instead pays ten band
+// rounds). So the frame is split at the only narrow point of the pipeline, the primitive list (~12 segments x 12 slots x 32 B):
+//   tc_prims_kernel       E envs per block like tc_render_envs_kernel - camera pass on the visible-set tables, set-up - but the
+//                         primitives go to global memory (L2) instead of being drawn;
+//   tc_draw_class_kernel  a block per (env, class): zero a full-frame plane, draw the env's primitives of that class, store the
+//                         plane; a class without segments (most `hold` / `area` / `solid` planes) is written as zeros at once.
+// Envs with more than TC_PRIMS_CAP segments (long camera ranges) are flagged and rendered by the banded kernel afterwards.
+#define TC_PRIMS_CAP 64
+#define TC_PRIMS_SEG_WORDS (TC_MAX_PRIMS_PER_SEG * 8)
+struct TcPrimsOut {
+    int32_t *prims;   // [N][TC_PRIMS_CAP][12][8]
+    uint8_t *tags;    // [N][TC_PRIMS_CAP] class of each segment
+    int32_t *count;   // [N] segments (0 for masked-out envs; > TC_PRIMS_CAP: overflow, nothing else written)
+    uint8_t *overflow;// [N] 1: the env needs the fallback kernel
+};
+
+template <int NT, int E>
+__global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_prims_kernel(const TcRenderEnvArgs a, const TcPrimsOut o) {
+    constexpr int TPE = NT / E;
+    constexpr int CAP = TC_ENVS_CHUNKS * TC_ENV_CHUNK;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int seg_cnt[E], s_pref[E + 1], s_thick[E], s_active[E];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double s_pose[E][12], s_cam[E][TC_CAM_N];
+    __shared__ TcCellBlob s_desc[E];
+    __shared__ int4 s_seg[CAP];
+    __shared__ uint16_t s_tag[CAP];   // env slot << 8 | class
+    __shared__ int s_gpos[CAP];       // index of the segment within its env
+    __shared__ int s_task, s_nseg, s_ntask;
+#define TC_REGION(e) (smem_raw + (size_t)(e) * a.region_bytes)
+#define TC_PW ((int32_t *)(smem_raw + (size_t)E * a.region_bytes))
+    if (threadIdx.x == 0) {
+        tc_mbar_init(&bar, E);
+        tc_fence_mbar_init();
+    }
+    __syncwarp();
+    if (threadIdx.x < E) {
+        const int e = threadIdx.x, env = blockIdx.x * E + e;
+        const bool act = env < a.n_envs && !(a.mask && !a.mask[env]);
+        TcCellBlob d;
+        if (act) d = a.cell_desc[tc_cull_cell(a.grid, a.pose + (size_t)env * 12)];
+        else { d.n_nodes = 0; d.n_edges = 0; d.bytes = 0; d.offset = 0; }
+        s_active[e] = act; seg_cnt[e] = 0; s_thick[e] = act ? a.thickness[env] : 1;
+        s_desc[e] = d;
+        if (d.bytes > 0) {
+            tc_mbar_expect_tx(&bar, (uint32_t)d.bytes);
+            tc_bulk_g2s(TC_REGION(e) + tc_env_off_tables((size_t)a.np), a.cell_blob + d.offset, (uint32_t)d.bytes, &bar);
+        } else tc_mbar_arrive(&bar);
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + E * 17) {
+        const int k = threadIdx.x - 32, e = k / 17, i = k % 17, env = blockIdx.x * E + e;
+        if (env < a.n_envs) {
+            if (i < 12) s_pose[e][i] = a.pose[(size_t)env * 12 + i];
+            else s_cam[e][TC_CAM_FX + i - 12] = a.cam[(size_t)env * TC_CAM_N + TC_CAM_FX + i - 12];
+        }
+    }
+    __syncthreads();
+    {
+        const int j = threadIdx.x / TPE;
+        tc_env_camera_pass<TPE>(TC_REGION(j), (size_t)a.np, TC_REGION(j) + tc_env_off_tables((size_t)a.np), s_desc[j], &bar, s_pose[j], s_cam[j], a.H, a.W,
+                                &seg_cnt[j], (int)threadIdx.x - j * TPE);
+    }
+    if (threadIdx.x < E) {
+        const int e = threadIdx.x, env = blockIdx.x * E + e;
+        if (env < a.n_envs) {
+            // masked-out envs keep their previous frame: the draw kernel skips them by the same mask, and the fallback kernel by a
+            // cleared overflow flag
+            const bool ovf = s_active[e] && seg_cnt[e] > TC_PRIMS_CAP;
+            if (s_active[e]) o.count[env] = seg_cnt[e];
+            o.overflow[env] = ovf ? 1 : 0;
+            if (ovf) seg_cnt[e] = 0;   // rendered by the fallback kernel: no set-up here
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int e = 0; e < E; e++) { s_pref[e] = acc; acc += seg_cnt[e]; }
+        s_pref[E] = acc;
+    }
+    __syncthreads();
+    for (int base = 0; base < s_pref[E]; base += a.prim_chunks * TC_ENV_CHUNK) {
+        {
+            const int nseg = min(a.prim_chunks * TC_ENV_CHUNK, s_pref[E] - base);
+            int32_t *pw = TC_PW;
+            for (int i = threadIdx.x; i < nseg * TC_MAX_PRIMS_PER_SEG; i += NT)
+                pw[(i / TC_MAX_PRIMS_PER_SEG) * TC_ENV_SEG_WORDS + (i % TC_MAX_PRIMS_PER_SEG) * 8] = TC_PRIM_NONE;
+            if ((int)threadIdx.x < nseg) {
+                const int sidx = base + threadIdx.x;
+                int e = 0;
+#pragma unroll
+                for (int k = 1; k < E; k++) e += sidx >= s_pref[k];
+                const int i = sidx - s_pref[e];
+                const int4 *segs = (const int4 *)TC_REGION(e);
+                const uint8_t cls = ((const uint8_t *)(segs + s_desc[e].n_edges))[i];
+                s_seg[threadIdx.x] = segs[i];
+                s_tag[threadIdx.x] = (uint16_t)((e << 8) | cls);
+                s_gpos[threadIdx.x] = i;
+                o.tags[(size_t)(blockIdx.x * E + e) * TC_PRIMS_CAP + i] = cls;
+            }
+            if (threadIdx.x == 0) {
+                s_task = 0; s_nseg = nseg;
+                s_ntask = ((nseg + TC_ENV_CHUNK - 1) / TC_ENV_CHUNK) * TC_N_ROLES;
+            }
+        }
+        __syncthreads();
+        while (true) {
+            int k = 0;
+            if ((threadIdx.x & 31) == 0) k = atomicAdd(&s_task, 1);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= s_ntask) break;
+            const int nchunks = s_ntask / TC_N_ROLES;
+            const int role = k / nchunks, sl = (k - role * nchunks) * TC_ENV_CHUNK + (threadIdx.x & 31);
+            if (sl < s_nseg) {
+                const int4 s4 = s_seg[sl];
+                tc_polyline_setup<true>(a.W, a.H, s4.x, s4.y, s4.z, s4.w, s_thick[s_tag[sl] >> 8], role, (TcPrim *)(TC_PW + sl * TC_ENV_SEG_WORDS));
+            }
+        }
+        __syncthreads();
+        // the round's primitives to global memory: consecutive threads write consecutive words of a segment's 12 slots
+        for (int i = threadIdx.x; i < s_nseg * TC_PRIMS_SEG_WORDS; i += NT) {
+            const int sl = i / TC_PRIMS_SEG_WORDS, wd = i - sl * TC_PRIMS_SEG_WORDS;
+            const int env = blockIdx.x * E + (s_tag[sl] >> 8);
+            o.prims[((size_t)env * TC_PRIMS_CAP + s_gpos[sl]) * TC_PRIMS_SEG_WORDS + wd] = TC_PW[sl * TC_ENV_SEG_WORDS + wd];
+        }
+        __syncthreads();
+    }
+#undef TC_REGION
+#undef TC_PW
+}
+
+struct TcDrawArgs {
+    int n_envs, n_classes, H, W;
+    int plane_words;          // words of one full-frame bit plane (incl. pad word)
+    const uint8_t *mask;      // optional
+    TcPrimsOut in;
+    uint8_t *obs;
+};
+
+// FMT: TC_FMT_BITS (u32 [N,C,H*W/32]); the block's plane is the output
+template <int NT, int FMT>
+__global__ void __launch_bounds__(NT) tc_draw_class_kernel(const TcDrawArgs a) {
+    extern __shared__ __align__(128) uint32_t plane[];
+    __shared__ int s_list[TC_PRIMS_CAP];   // this class's segments
+    __shared__ int s_n;
+    const int env = blockIdx.x / a.n_classes, c = blockIdx.x - env * a.n_classes;
+    if (a.mask && !a.mask[env]) return;
+    if (a.in.overflow[env]) return;        // the fallback kernel renders this env
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cnt = a.in.count[env];
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    if (tid < cnt && a.in.tags[(size_t)env * TC_PRIMS_CAP + tid] == c) s_list[atomicAdd(&s_n, 1)] = tid;
+    __syncthreads();
+    const int n = s_n;
+    const size_t frame_words = ((size_t)a.H * a.W + 31) / 32;
+    uint32_t *out = (uint32_t *)a.obs + ((size_t)env * a.n_classes + c) * frame_words;
+    if (n == 0) {   // nothing of this class in view: the plane is zeros
+        if ((frame_words & 3) == 0) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (size_t i = tid; i < frame_words / 4; i += NT) tc_st_cs((uint4 *)out + i, z);
+        } else
+            for (size_t i = tid; i < frame_words; i += NT) out[i] = 0u;
+        return;
+    }
+    for (int i = tid; i < a.plane_words; i += NT) plane[i] = 0;
+    __syncthreads();
+    const TcPlane pl = {plane, a.H, a.W, 0, a.H, 0};
+    const TcLanes g = {lane, 32}, g1 = {0, 1};
+    const int32_t *base = a.in.prims + (size_t)env * TC_PRIMS_CAP * TC_PRIMS_SEG_WORDS;
+    // one thread per primitive slot of the class's segments; long primitives are handed to the whole warp (as in tc_render_env_kernel)
+    // (slot p goes to warp p % (NT/32): a class has a few long primitives, and a warp draws its long ones one after the other)
+    const int rounds = (n * TC_MAX_PRIMS_PER_SEG + NT - 1) / NT;
+    for (int r = 0; r < rounds; r++) {
+        const int p = r * NT + lane * (NT / 32) + (tid >> 5);
+        TcPrim q;
+        q.kind = TC_PRIM_NONE;
+        if (p < n * TC_MAX_PRIMS_PER_SEG) {
+            const int4 *src = (const int4 *)(base + (size_t)s_list[p / TC_MAX_PRIMS_PER_SEG] * TC_PRIMS_SEG_WORDS + (p % TC_MAX_PRIMS_PER_SEG) * 8);
+            const int4 lo = src[0];
+            q.kind = lo.x; q.a[0] = lo.y; q.a[1] = lo.z; q.a[2] = lo.w;
+            if (q.kind != TC_PRIM_NONE) {
+                const int4 hi = src[1];
+                q.a[3] = hi.x; q.a[4] = hi.y; q.a[5] = hi.z; q.a[6] = hi.w;
+            }
+        }
+        const int items = q.kind != TC_PRIM_NONE ? tc_prim_items(q) : 0;
+        unsigned big = __ballot_sync(0xffffffffu, items > TC_SMALL_PRIM_ITEMS);
+        if (items > 0 && items <= TC_SMALL_PRIM_ITEMS) tc_prim_draw(g1, pl, q);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            TcPrim w;
+            w.kind = __shfl_sync(0xffffffffu, q.kind, src);
+#pragma unroll
+            for (int k = 0; k < 7; k++) w.a[k] = __shfl_sync(0xffffffffu, q.a[k], src);
+            tc_prim_draw(g, pl, w);
+        }
+    }
+    __syncthreads();
+    if ((frame_words & 3) == 0) {
+        for (size_t i = tid; i < frame_words / 4; i += NT) tc_st_cs((uint4 *)out + i, ((const uint4 *)plane)[i]);
+    } else
+        for (size_t i = tid; i < frame_words; i += NT) out[i] = plane[i];
+}
+
 // ------------------------------------------------------------------------------------------------ fused, block per env, banded
 // Large frames in the formats whose stores are NOT the bound - RGB (composition work per byte) and 1 bit per pixel (8x fewer
 // bytes): a block owns a whole frame. Camera pass on the visible-set sub-graph as in tc_render_env_kernel, set-up of all
@@ -1412,8 +1619,11 @@ __host__ __device__ inline size_t tc_envb_smem_bytes(size_t np, int max_bytes, i
     return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
+#ifndef TC_ENVB_MIN_BLOCKS
+#define TC_ENVB_MIN_BLOCKS 4
+#endif
 template <int FMT>
-__global__ void __launch_bounds__(256, 4) tc_render_env_banded_kernel(const TcRenderEnvArgs a) {
+__global__ void __launch_bounds__(256, TC_ENVB_MIN_BLOCKS) tc_render_env_banded_kernel(const TcRenderEnvArgs a) {
     constexpr int NT = 256;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int seg_cnt;
@@ -1425,17 +1635,22 @@ __global__ void __launch_bounds__(256, 4) tc_render_env_banded_kernel(const TcRe
     __shared__ uint16_t list[TC_RGBE_MAX_SEGS * TC_MAX_PRIMS_PER_SEG];
     __shared__ int list_n;
     __shared__ unsigned band_mask;
-    const int env = blockIdx.x;
-    if (a.mask && !a.mask[env]) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = a.n_classes;
     const size_t np = (size_t)a.np;
     unsigned char *tab_smem = smem_raw + tc_env_off_tables(np);
     if (tid == 0) {
-        const TcCellBlob d = a.cell_desc[tc_cull_cell(a.grid, a.pose + (size_t)env * 12)];
-        seg_cnt = 0;
         tc_mbar_init(&bar, 1);
         tc_fence_mbar_init();
+    }
+    uint32_t phase = 0;   // parity of the mbarrier's current phase: one TMA copy per rendered env
+    // the grid may be smaller than the env count (the fallback launch of the two-kernel path scans a sparse mask with few blocks)
+    for (int env = blockIdx.x; env < a.n_envs; env += gridDim.x) {
+    if (a.mask && !a.mask[env]) continue;
+    __syncthreads();   // the previous env's shared state is dead (and the barrier initialised)
+    if (tid == 0) {
+        const TcCellBlob d = a.cell_desc[tc_cull_cell(a.grid, a.pose + (size_t)env * 12)];
+        seg_cnt = 0;
         if (d.bytes > 0) {
             tc_mbar_expect_tx(&bar, (uint32_t)d.bytes);
             tc_bulk_g2s(tab_smem, a.cell_blob + d.offset, (uint32_t)d.bytes, &bar);
@@ -1451,7 +1666,10 @@ __global__ void __launch_bounds__(256, 4) tc_render_env_banded_kernel(const TcRe
     uint32_t *planes = (uint32_t *)(smem_raw + np * 24);
     uint32_t *any_plane = (uint32_t *)(smem_raw + tc_envb_off_any(np, C, a.band_words));
     int32_t *pw = (int32_t *)(smem_raw + tc_envb_off_prims(np, C, a.band_words));
-    if (n > 0) tc_env_camera_pass<NT>(smem_raw, np, tab_smem, s_desc, &bar, s_pose, s_cam, a.H, a.W, &seg_cnt);
+    if (n > 0) {
+        tc_env_camera_pass<NT>(smem_raw, np, tab_smem, s_desc, &bar, s_pose, s_cam, a.H, a.W, &seg_cnt, threadIdx.x, s_desc.bytes > 0 ? phase : 0xffffffffu);
+        if (s_desc.bytes > 0) phase ^= 1u;
+    }
     const int total = seg_cnt;
     const uint8_t *seg_cls = (const uint8_t *)(segs + m);
     const int t = a.thickness[env];
@@ -1541,6 +1759,7 @@ __global__ void __launch_bounds__(256, 4) tc_render_env_banded_kernel(const TcRe
                 for (int i = tid; i < words; i += NT) o[(size_t)c * frame_words + i] = drew ? planes[(size_t)c * a.band_words + i] : 0u;
         }
         __syncthreads();   // the next band reuses the planes
+    }
     }
 }
 
