@@ -124,6 +124,11 @@ TC_API int tc_set_car_params(TcHandle *h, const double *dev_params /*[N,TC_CP_N]
 /* Handles that render small frames with one block per env (C*H*W <= 128 KB) read the rows back in this call and rebuild
  * their visible-set tables when the cameras' reach changed: the call then synchronises the stream (it is a set-up call). */
 TC_API int tc_set_camera_params(TcHandle *h, const double *dev_cam /*[N,TC_CAM_N]*/, const int32_t *dev_thickness /*[N]*/, void *stream);
+/* The same with the caller's HOST copy of the rows (host_cam [N,TC_CAM_N], may be NULL): how far the cameras see decides which
+ * visible-set tables the small-frame render kernels use, and with the host copy that decision needs no read-back, so the
+ * call does not synchronise. Tables are built on the host once per camera reach (~50-150 ms for a map like Knuffingen) and
+ * kept: returning to an earlier reach - Camera.update_params() per episode, examples/train_stanley_il.py:52-57 - costs nothing. */
+TC_API int tc_set_camera_params_host(TcHandle *h, const double *dev_cam, const int32_t *dev_thickness, const double *host_cam, void *stream);
 TC_API int tc_set_wrapped(TcHandle *h, int32_t wrapped); /* 1: reward 0 / terminated false (env.py:137-138) */
 
 /* Spawn streams on the device (Map.sample_spawn's draw, map.py:61-64, under gymnasium seeding): dev_rng_state is uint64
@@ -202,6 +207,8 @@ TC_API int tc_debug_cull_info(TcHandle *h, double *host_out4);
 /* Diagnostics: which kernels this handle launches. out8 = {block-per-env render path (0/1), envs per block of the packed
  * kernel (0: one-env kernel), its 32-segment chunks, dynamic shared memory of the render kernel, thread-per-env tracking (0/1),
  * shared memory of the banded kernel (0: unused), node capacity and table bytes of the visible-set cells}. */
+/* out4 = {visible-set table builds, cache hits, host milliseconds of the last build, of all builds} */
+TC_API int tc_debug_cull_stats(TcHandle *h, double *out4);
 TC_API int tc_debug_render_info(TcHandle *h, int32_t *out8);
 
 /* Test hook: the reference's Layer queries (layer.py) evaluated by the DEVICE functions on class 0 of the handle's map.

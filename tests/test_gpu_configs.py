@@ -343,3 +343,134 @@ def test_gym_make_with_a_gymnasium_on_the_path():
     envv = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "golden", "gym_stub"), ROOT]))
     out = subprocess.run([sys.executable, "-c", code], env=envv, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "gym.make ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_cuda_camera_randomisation_reuses_tables():
+    """Per-episode camera randomisation (examples/train_stanley_il.py:52-57): the visible-set tables are built once per reach step
+    and kept, so alternating between camera settings neither rebuilds on the host nor synchronises; frames stay the oracle's."""
+    n = 96
+    cfg = make_config("knuffingen", "classes", cam={"resolution": [96, 128]})
+    env = _vec(cfg, n)
+    rng = np.random.default_rng(3)
+    settings = [dict(fov=80.0, max_range=0.5, pitch=22.0), dict(fov=120.0, max_range=0.9, pitch=12.0), dict(fov=95.0, max_range=0.55, pitch=18.0)]
+    builds_after_first_cycle = None
+    for ep in range(9):
+        s_ = settings[ep % 3]
+        env.set_camera_params(orientation=np.array([s_["pitch"], 0.0, 0.0]), fov=s_["fov"], max_range=s_["max_range"])
+        oenv = oracle_env(cfg, n, cam_rows=env._cam_rows.copy())
+        env.reset(seed=ep)
+        oenv.reset(env._spawn_nodes.cpu().numpy())
+        assert np.array_equal(env.obs.cpu().numpy(), oenv.obs), ep
+        for t in range(3):
+            cc = np.stack([rng.uniform(0.3, 1, n), rng.uniform(-1, 1, n)], 1).astype(np.float32)
+            man = np.zeros(n, np.int32)
+            env.step({"car_control": torch.from_numpy(cc).cuda(), "maneuver": torch.from_numpy(man).cuda()})
+            oenv.step(cc.astype(np.float64), man)
+            assert np.array_equal(env.obs.cpu().numpy(), oenv.obs), (ep, t)
+        if ep == 2:
+            builds_after_first_cycle = env.cull_stats()["builds"]
+    st = env.cull_stats()
+    print("cull stats:", st, env.cull_info())
+    assert st["builds"] == builds_after_first_cycle <= 4, st     # the whole-graph set of construction + at most one per setting
+    assert st["cache_hits"] >= 4, st
+    env.close()
+
+
+@pytest.mark.parametrize("case", ["packed128", "oneenv128", "packed84", "rgb96", "env240", "classes480", "rgb480", "bits480", "bits480_overflow", "bf16_128"])
+def test_cuda_guard_bands_determinism_and_full_overwrite(case):
+    """compute-sanitizer is closed on this GPU pool, so the memory-safety evidence is made here, per render path:
+    * guard bands: the observation and every per-env output live inside larger buffers whose surroundings are filled with a sentinel;
+      after stepping, the sentinels must be intact (an out-of-bounds store of a render / tracking kernel would hit them);
+    * full overwrite: the observation buffer is poisoned with 0xAB before every step and must come back holding only legal values and
+      exactly the oracle's frame (a store the kernel skipped, or one fed from uninitialised shared memory, shows up here);
+    * determinism: the same step from the same state, 6 times over, gives bit-identical frames and outputs (the kernels overlay
+      shared-memory regions and draw with atomicOr: a missing barrier would make results depend on timing)."""
+    import os
+    setenv, kw, n = {}, {}, 24
+    if case == "packed128":
+        cfg = make_config("knuffingen", "classes", cam={"resolution": [128, 160]}); n = 37
+    elif case == "oneenv128":
+        cfg = make_config("knuffingen", "classes", cam={"resolution": [128, 160]}); setenv = {"TC_ENV_PACK": "0"}; n = 19
+    elif case == "packed84":
+        cfg = make_config("simple_layout", "classes", cam={"resolution": [84, 84]}, car={"max_velocity": 0.15}); n = 41
+    elif case == "rgb96":
+        cfg = make_config("simple_layout", "rgb", cam={"resolution": [96, 128]}, car={"max_velocity": 0.15}); n = 21
+    elif case == "env240":
+        cfg = make_config("knuffingen", "classes", cam={"resolution": [240, 320]}); n = 9
+    elif case == "classes480":
+        cfg = make_config("knuffingen", "classes", cam={"resolution": [480, 640]}); n = 5
+    elif case == "rgb480":
+        cfg = make_config("simple_layout", "rgb", cam={"resolution": [480, 640]}, car={"max_velocity": 0.15}); n = 5
+    elif case == "bits480":
+        cfg = make_config("knuffingen", "classes", cam={"resolution": [480, 640]}); kw = {"obs_format": "classes_bits"}; n = 7
+    elif case == "bits480_overflow":
+        cfg = make_config("simple_layout", "classes", cam={"resolution": [480, 640], "max_range": 3.0, "orientation": [30, 0, 0]}, car={"max_velocity": 0.15})
+        kw = {"obs_format": "classes_bits"}; n = 5
+    else:
+        cfg = make_config("knuffingen", "classes", cam={"resolution": [128, 160]}); kw = {"obs_format": "classes_bf16"}; n = 11
+    old = {k: os.environ.get(k) for k in setenv}
+    os.environ.update(setenv)
+    try:
+        env = _vec(cfg, n, **kw)
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    oenv = oracle_env(cfg, n)
+    H, W = cfg["camera"]["resolution"]
+    # ---- move every output into a guarded buffer: [guard | payload | guard], sentinel bytes 0x5C
+    G = 4096
+    guards = []
+
+    def guarded(t):
+        nb = t.numel() * t.element_size()
+        pad = (-nb) % 16
+        buf = torch.full((G + nb + pad + G,), 0x5C, dtype=torch.uint8, device=t.device)
+        view = buf[G:G + nb].view(t.dtype).view(t.shape)
+        view.copy_(t)
+        guards.append((buf, nb))
+        return view
+    env.obs = guarded(env.obs)
+    for k in list(env.out):
+        env.out[k] = guarded(env.out[k])
+    env._outs = env._make_outputs(with_obs=True)
+    env._outs_noobs = env._make_outputs(with_obs=False)
+
+    def decode(obs):
+        if kw.get("obs_format") == "classes_bf16":
+            f = obs.float().cpu().numpy()
+            assert set(np.unique(f)).issubset({0.0, 1.0})
+            return (f * 255).astype(np.uint8)
+        o = obs.cpu().numpy()
+        if kw.get("obs_format") == "classes_bits":
+            return np.unpackbits(o.view(np.uint32).view(np.uint8), axis=-1, bitorder="little")[..., : H * W].reshape(n, -1, H, W) * 255
+        return o
+    rng = np.random.default_rng(11)
+    env.obs.view(torch.uint8).fill_(0xAB)
+    env.reset(seed=8)
+    oenv.reset(env._spawn_nodes.cpu().numpy())
+    assert np.array_equal(decode(env.obs), oenv.obs), "reset frames"
+    for t in range(4):
+        cc = torch.from_numpy(np.stack([rng.uniform(0.3, 1, n), rng.uniform(-1, 1, n)], 1).astype(np.float32)).cuda()
+        man = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)).cuda()
+        st0 = {k: v.clone() for k, v in env.state_dict().items()}
+        first = None
+        for rep in range(6):            # the same step six times from the same state
+            env.load_state_dict(st0)
+            env.obs.view(torch.uint8).fill_(0xAB)
+            env.step({"car_control": cc, "maneuver": man})
+            snap = (env.obs.clone(), env.out["info_f64"].clone(), env.out["nearest_edge"].clone(), env.out["truncated"].clone())
+            if first is None:
+                first = snap
+            else:
+                assert all(torch.equal(a, b) for a, b in zip(first, snap)), f"step {t} repetition {rep} differs: the kernels are not deterministic"
+        oenv.step(cc.cpu().numpy().astype(np.float64), man.cpu().numpy())
+        assert np.array_equal(decode(env.obs), oenv.obs), f"frames at step {t}"
+        done = (oenv.terminated | oenv.truncated).astype(bool)
+        if done.any():
+            env.reset_done()
+            oenv.reset(env._spawn_nodes.cpu().numpy(), mask=done)
+            assert np.array_equal(decode(env.obs), oenv.obs), f"frames after the reset at step {t}"
+    torch.cuda.synchronize()
+    for buf, nb in guards:
+        assert bool((buf[:G] == 0x5C).all()) and bool((buf[G + nb + ((-nb) % 16):] == 0x5C).all()), "a kernel wrote outside an output buffer"
+    env.close()

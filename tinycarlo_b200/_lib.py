@@ -116,6 +116,8 @@ def lib():
     L.tc_destroy.argtypes = [vp]
     L.tc_set_car_params.argtypes = [vp, vp, vp]
     L.tc_set_camera_params.argtypes = [vp, vp, vp, vp]
+    L.tc_set_camera_params_host.argtypes = [vp, vp, vp, vp, vp]
+    L.tc_debug_cull_stats.argtypes = [vp, C.POINTER(C.c_double)]
     L.tc_set_wrapped.argtypes = [vp, i32]
     L.tc_set_autoreset.argtypes = [vp, vp]
     L.tc_set_reset_mask.argtypes = [vp, vp]
@@ -137,7 +139,7 @@ def lib():
     L.tc_profile_begin.argtypes = [vp, i32]
     L.tc_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32)]
     L.tc_debug_layer_query.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double, i32, i32, vp, vp, vp]
-    for name in ("tc_debug_render_info", "tc_step_host_obs", "tc_set_reset_mask", "tc_debug_cull_info", "tc_set_spawn_rng", "tc_noise_blobs", "tc_step_f64", "tc_debug_set_timeline", "tc_set_autoreset", "tc_create", "tc_destroy", "tc_set_car_params", "tc_set_camera_params", "tc_set_wrapped", "tc_reset", "tc_step",
+    for name in ("tc_set_camera_params_host", "tc_debug_cull_stats", "tc_debug_render_info", "tc_step_host_obs", "tc_set_reset_mask", "tc_debug_cull_info", "tc_set_spawn_rng", "tc_noise_blobs", "tc_step_f64", "tc_debug_set_timeline", "tc_set_autoreset", "tc_create", "tc_destroy", "tc_set_car_params", "tc_set_camera_params", "tc_set_wrapped", "tc_reset", "tc_step",
                  "tc_render", "tc_get_state", "tc_set_state", "tc_step_host", "tc_debug_layer_query", "tc_profile_begin", "tc_profile_end"):
         getattr(L, name).restype = C.c_int
     if L.tc_abi_version() != 1:

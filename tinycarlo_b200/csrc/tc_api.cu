@@ -2,6 +2,7 @@
 // Host side: table packing/staging, per-env device buffers, launch configuration. No torch, no CPU compute path.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -33,6 +34,20 @@ static int tc_fail(int code, const std::string &msg) {
         cudaError_t _e = (expr);                                                                                             \
         if (_e != cudaSuccess) return tc_fail(TC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
     } while (0)
+
+// One set of visible-set tables on the device (tc_cull.h) with the launch geometry derived from it. A handle keeps the sets it
+// has built (by the camera reach they were built for), so that returning to an earlier reach - per-episode camera randomisation
+// through the single-env drop-in - neither rebuilds on the host nor allocates nor synchronises.
+struct TcCullSet {
+    double key = -1.0;                 // the reach asked for
+    TcCellBlob *d_desc = nullptr;
+    unsigned char *d_blob = nullptr;
+    TcCullGrid grid{};
+    int np = 0, max_bytes = 0, cells = 0, max_nodes = 0;
+    size_t env_smem = 0, envb_smem = 0, envs_smem = 0;
+    int pack = 0, chunks = 1, blocks = 0;
+    double radius = -1.0, mean_nodes = 0.0;
+};
 
 struct TcHandle {
     int device = 0;
@@ -83,6 +98,10 @@ struct TcHandle {
     TcCellBlob *d_cell_desc = nullptr;
     unsigned char *d_cell_blob = nullptr;
     TcCullGrid cull_grid{};
+    std::vector<TcCullSet> cull_sets;   // every set built so far (freed by tc_destroy)
+    double cull_key = -2.0;             // the active one
+    int cull_builds = 0, cull_hits = 0;
+    double cull_build_ms_last = 0.0, cull_build_ms_total = 0.0;
     int env_np = 0, env_max_bytes = 0, env_words = 0;
     size_t env_smem = 0;     // tc_render_env_kernel (small frames)
     // two-kernel path of large bit-packed frames (tc_prims_kernel + tc_draw_class_kernel): buffers allocated at first use
@@ -146,47 +165,59 @@ static TcMapDesc tc_host_map(const TcHandle *h) {
     m.ll_nodes = h->m_nodes.data(); m.ll_edges = h->m_edges.data();
     return m;
 }
-// (re)builds the visible-set tables for camera reach `radius` (< 0: culling off) and moves them to the device
+// makes the visible-set tables for camera reach `radius` (< 0: culling off) the active ones: from the handle's cache, or built
+// on the host (tc_cull.h, ~50-150 ms for Knuffingen) and copied to the device. Never frees tables a running kernel may read.
+static void tc_activate_cull(TcHandle *h, const TcCullSet &c) {
+    h->d_cell_desc = c.d_desc; h->d_cell_blob = c.d_blob;
+    h->cull_grid = c.grid; h->env_np = c.np; h->env_max_bytes = c.max_bytes; h->env_smem = c.env_smem; h->envb_smem = c.envb_smem;
+    h->cull_radius = c.radius; h->cull_mean_nodes = c.mean_nodes; h->cull_cells = c.cells; h->cull_max_nodes = c.max_nodes;
+    h->env_pack = c.pack; h->env_chunks = c.chunks; h->envs_smem = c.envs_smem; h->env_blocks = c.blocks;
+    h->cull_key = c.key;
+}
 static int tc_install_cull(TcHandle *h, double radius) {
+    if (const char *ce = getenv("TC_CULL")) if (atoi(ce) == 0) radius = -1.0;
+    for (const TcCullSet &c : h->cull_sets)
+        if (c.key == radius) {
+            tc_activate_cull(h, c);
+            h->cull_hits++;
+            return TC_OK;
+        }
+    const auto t0 = std::chrono::steady_clock::now();
     TcCull cull;
     TcMapDesc m = tc_host_map(h);
     double cell = 0.25;
     if (const char *cs = getenv("TC_CULL_CELL")) cell = atof(cs) > 0 ? atof(cs) : cell;
-    if (const char *ce = getenv("TC_CULL")) if (atoi(ce) == 0) radius = -1.0;
     tc_build_cull(&m, radius, cell, 0.05, cull);
+    TcCullSet c;
+    c.key = radius;
     const size_t np = tc_env_np(cull.max_nodes, cull.max_edges);
     const size_t smem = h->fused_all ? tc_env_smem_bytes(np, cull.max_bytes, h->env_words) : 0;
     if (smem > 200 * 1024) return tc_fail(TC_ERR_INVALID, "visible-set tables exceed the shared-memory budget");
     size_t smem_b = h->fused_all ? 0 : tc_envb_smem_bytes(np, cull.max_bytes, h->C, h->envb_words);
     if (smem_b > 110 * 1024 || (h->envb_rows * h->W) % 32 != 0 || h->envb_bands > 1024) smem_b = 0;   // not worth it / not word aligned: other paths
-    TcCellBlob *dd = nullptr;
-    unsigned char *db = nullptr;
-    TC_CUDA(cudaMalloc((void **)&dd, cull.desc.size() * sizeof(TcCellBlob)));
-    cudaError_t e = cudaMalloc((void **)&db, std::max<size_t>(cull.blob.size(), 16));
-    if (e != cudaSuccess) { cudaFree(dd); return tc_fail(TC_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
-    TC_CUDA(cudaDeviceSynchronize());   // kernels that still read the old tables
-    TC_CUDA(cudaMemcpy(dd, cull.desc.data(), cull.desc.size() * sizeof(TcCellBlob), cudaMemcpyHostToDevice));
-    if (!cull.blob.empty()) TC_CUDA(cudaMemcpy(db, cull.blob.data(), cull.blob.size(), cudaMemcpyHostToDevice));
-    cudaFree(h->d_cell_desc);
-    cudaFree(h->d_cell_blob);
-    h->d_cell_desc = dd; h->d_cell_blob = db;
+    TC_CUDA(cudaMalloc((void **)&c.d_desc, cull.desc.size() * sizeof(TcCellBlob)));
+    cudaError_t e = cudaMalloc((void **)&c.d_blob, std::max<size_t>(cull.blob.size(), 16));
+    if (e != cudaSuccess) { cudaFree(c.d_desc); return tc_fail(TC_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    h->cull_sets.push_back(c);   // owned by the handle from here on (tc_destroy frees it)
+    TC_CUDA(cudaMemcpy(c.d_desc, cull.desc.data(), cull.desc.size() * sizeof(TcCellBlob), cudaMemcpyHostToDevice));
+    if (!cull.blob.empty()) TC_CUDA(cudaMemcpy(c.d_blob, cull.blob.data(), cull.blob.size(), cudaMemcpyHostToDevice));
     {
         // The packed small-frame kernel (tc_render_envs_kernel, 3 blocks of 256 threads per SM): E envs per block and 1 or 2
         // 32-segment chunks of primitive slots, chosen for the most envs in flight per SM without dropping below 2 blocks per SM
         // (fewer blocks hide the latency-bound phases worse than fuller lanes gain); E = 1 never beats tc_render_env_kernel
         // (measured), which stays the fallback. TC_ENV_PACK=0|2|4 and TC_ENV_CHUNKS=1|2 override.
-        int pack = 0, chunks = 1;
+        int pack = 0, chunks = 1, nblocks = 0;
         if (h->fused_all) {
             int best = 0;
-            for (int e : {2, 4})
-                for (int c : {2, 1}) {
-                    const size_t sm = tc_envs_smem_bytes(e, np, cull.max_bytes, h->env_words, c);
+            for (int ee : {2, 4})
+                for (int cc : {2, 1}) {
+                    const size_t sm = tc_envs_smem_bytes(ee, np, cull.max_bytes, h->env_words, cc);
                     if (sm > 200 * 1024) continue;
                     int blocks = 0;   // what the device really keeps resident (registers, static + reserved shared memory, carve-out steps)
-                    cudaError_t oe = e == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tc_render_envs_kernel<256, TC_FMT_U8, 2>, 256, sm)
-                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tc_render_envs_kernel<256, TC_FMT_U8, 4>, 256, sm);
+                    cudaError_t oe = ee == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tc_render_envs_kernel<256, TC_FMT_U8, 2>, 256, sm)
+                                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tc_render_envs_kernel<256, TC_FMT_U8, 4>, 256, sm);
                     if (oe != cudaSuccess) { cudaGetLastError(); continue; }
-                    if (blocks >= (e == 2 ? 2 : 3) && e * blocks > best) { best = e * blocks; pack = e; chunks = c; h->env_blocks = blocks; }
+                    if (blocks >= (ee == 2 ? 2 : 3) && ee * blocks > best) { best = ee * blocks; pack = ee; chunks = cc; nblocks = blocks; }
                 }
             if (const char *pe = getenv("TC_ENV_PACK")) {
                 const int v = atoi(pe);
@@ -195,11 +226,16 @@ static int tc_install_cull(TcHandle *h, double radius) {
             if (const char *pc = getenv("TC_ENV_CHUNKS")) chunks = atoi(pc) == 2 ? 2 : 1;
             if (pack && tc_envs_smem_bytes(pack, np, cull.max_bytes, h->env_words, chunks) > 200 * 1024) pack = 0;
         }
-        h->env_pack = pack; h->env_chunks = chunks;
-        h->envs_smem = pack ? tc_envs_smem_bytes(pack, np, cull.max_bytes, h->env_words, chunks) : 0;
+        c.pack = pack; c.chunks = chunks; c.blocks = nblocks;
+        c.envs_smem = pack ? tc_envs_smem_bytes(pack, np, cull.max_bytes, h->env_words, chunks) : 0;
     }
-    h->cull_grid = cull.grid; h->env_np = (int)np; h->env_max_bytes = cull.max_bytes; h->env_smem = smem; h->envb_smem = smem_b;
-    h->cull_radius = cull.radius; h->cull_mean_nodes = cull.mean_nodes; h->cull_cells = (int)cull.desc.size(); h->cull_max_nodes = cull.max_nodes;
+    c.grid = cull.grid; c.np = (int)np; c.max_bytes = cull.max_bytes; c.env_smem = smem; c.envb_smem = smem_b;
+    c.radius = cull.radius; c.mean_nodes = cull.mean_nodes; c.cells = (int)cull.desc.size(); c.max_nodes = cull.max_nodes;
+    h->cull_sets.back() = c;
+    tc_activate_cull(h, c);
+    h->cull_builds++;
+    h->cull_build_ms_last = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    h->cull_build_ms_total += h->cull_build_ms_last;
     return TC_OK;
 }
 
@@ -216,8 +252,7 @@ int tc_destroy(TcHandle *h) {
     if (!h) return TC_OK;
     cudaSetDevice(h->device);
     for (void *p : h->allocs) cudaFree(p);
-    cudaFree(h->d_cell_desc);
-    cudaFree(h->d_cell_blob);
+    for (TcCullSet &c : h->cull_sets) { cudaFree(c.d_desc); cudaFree(c.d_blob); }
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     delete h;
     return TC_OK;
@@ -357,7 +392,8 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
         const size_t smem_one = tc_render_smem_bytes(h->max_nodes, h->max_edges, h->max_cblob_bytes, h->plane_words_full);
         // measured (Knuffingen 240x320, 8192 envs): block per env 0.56 ms against 1.05 ms for the per-class blocks, which pay the
         // camera pass and the set-up once per class; beyond ~75 KB a block (3 per SM) the per-class kernel's finer blocks win again
-        bool all = smem_all <= 100 * 1024 && tc_env_smem_bytes(tc_env_np(whole.max_nodes, whole.max_edges), whole.max_bytes, words_all) <= 76 * 1024;
+        // (the camera reach, hence the size of the visible-set tables, is not known yet: the plane is what decides)
+        bool all = smem_all <= 100 * 1024 && (size_t)words_all * 4 <= 50 * 1024;
         if (const char *fa = getenv("TC_FUSED_ALL")) all = atoi(fa) != 0 && smem_all <= 200 * 1024;
         h->fused_all = all ? 1 : 0;
         h->fused_nodes = h->max_nodes; h->fused_edges = h->max_edges;
@@ -420,29 +456,44 @@ int tc_set_car_params(TcHandle *h, const double *dev_params, void *stream) {
     return TC_OK;
 }
 
+// reach of the tables to use for cameras that see `radius` far: the first tables of a handle are tight; later ones go up to the
+// next step of a geometric ladder (x1.25), so that a reach that keeps changing (camera randomisation per episode) lands on a few
+// cached sets instead of a rebuild per change. Tables built for a larger reach are exact for a smaller one, only less tight.
+static double tc_cull_ladder(double radius) {
+    const double r0 = 0.05;
+    if (!(radius > r0)) return r0;
+    return r0 * std::pow(1.25, std::ceil(std::log(radius / r0) / std::log(1.25) - 1e-9));
+}
+
 int tc_set_camera_params(TcHandle *h, const double *dev_cam, const int32_t *dev_thickness, void *stream) {
+    return tc_set_camera_params_host(h, dev_cam, dev_thickness, nullptr, stream);
+}
+
+int tc_set_camera_params_host(TcHandle *h, const double *dev_cam, const int32_t *dev_thickness, const double *host_cam, void *stream) {
     if (!h || !dev_cam || !dev_thickness) return tc_fail(TC_ERR_INVALID, "tc_set_camera_params: null argument");
     TC_CUDA(cudaSetDevice(h->device));
     TC_CUDA(cudaMemcpyAsync(h->d_cam, dev_cam, (size_t)h->n_envs * TC_CAM_N * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     TC_CUDA(cudaMemcpyAsync(h->d_thick, dev_thickness, (size_t)h->n_envs * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     h->cam_set = true;
-    if (h->fused_all || h->envb_smem > 0 || h->cull_radius >= 0) {
-        // the visible-set tables depend on how far the cameras see: read the rows back (this call synchronises) and rebuild
-        std::vector<double> rows((size_t)h->n_envs * TC_CAM_N);
-        TC_CUDA(cudaMemcpyAsync(rows.data(), h->d_cam, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-        TC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (h->fused_all || h->envb_smem > 0 || h->cull_radius >= 0 || !h->cull_sets.empty()) {
+        // the visible-set tables depend on how far the cameras see: from the caller's host copy of the rows, or read back (synchronises)
+        std::vector<double> rows;
+        if (!host_cam) {
+            rows.resize((size_t)h->n_envs * TC_CAM_N);
+            TC_CUDA(cudaMemcpyAsync(rows.data(), h->d_cam, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+            TC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+            host_cam = rows.data();
+        }
         double radius = 0.0;
         for (int i = 0; i < h->n_envs && radius >= 0; i++) {
-            double r = tc_cull_radius_of(rows.data() + (size_t)i * TC_CAM_N, h->H, h->W);
+            double r = tc_cull_radius_of(host_cam + (size_t)i * TC_CAM_N, h->H, h->W);
             radius = r < 0 ? -1.0 : std::max(radius, r);
         }
-        // Tables built for a larger reach stay exact for a smaller one (only less tight): rebuild when the cameras see farther
-        // than the tables allow, or less than half as far. The first tables are tight; when the reach keeps changing (camera
-        // randomisation per episode through the single-env drop-in) later ones get 25 % headroom so that rebuilds die out.
+        // keep the active tables while they cover the cameras and are not more than twice too wide
         const bool keep = radius >= 0 && h->cull_radius >= radius && h->cull_radius <= 2.0 * radius;
         if (radius != h->cull_radius && !keep) {
             const bool first = !h->cull_built_once;
-            TC_TRY(tc_install_cull(h, radius < 0 || first ? radius : 1.25 * radius));
+            TC_TRY(tc_install_cull(h, radius < 0 || first ? radius : tc_cull_ladder(radius)));
             h->cull_built_once = true;
         }
     }
@@ -771,6 +822,12 @@ int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline) {
 int tc_debug_cull_info(TcHandle *h, double *out4) {
     if (!h || !out4) return tc_fail(TC_ERR_INVALID, "tc_debug_cull_info: null argument");
     out4[0] = (h->fused_all || h->envb_smem > 0) ? h->cull_radius : -2.0; out4[1] = h->cull_cells; out4[2] = h->cull_mean_nodes; out4[3] = h->cull_max_nodes;
+    return TC_OK;
+}
+
+int tc_debug_cull_stats(TcHandle *h, double *out4) {
+    if (!h || !out4) return tc_fail(TC_ERR_INVALID, "tc_debug_cull_stats: null argument");
+    out4[0] = h->cull_builds; out4[1] = h->cull_hits; out4[2] = h->cull_build_ms_last; out4[3] = h->cull_build_ms_total;
     return TC_OK;
 }
 

@@ -150,13 +150,17 @@ class TinyCarloVecEnv:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _upload_params(self):
+        """Car and camera rows to the device. Nothing here waits for the device: the library decides from the host copy of the
+        camera rows which visible-set tables to use (tc_set_camera_params_host) and keeps the tables it has built."""
         with torch.cuda.device(self.device):
             car = torch.from_numpy(self._car_rows).to(self.device)
             cam = torch.from_numpy(self._cam_rows).to(self.device)
             th = torch.from_numpy(self._thickness).to(self.device)
+            rows = np.ascontiguousarray(self._cam_rows, np.float64)
             _lib.check(self._L.tc_set_car_params(self._h, _ptr(car), self._stream()), "tc_set_car_params")
-            _lib.check(self._L.tc_set_camera_params(self._h, _ptr(cam), _ptr(th), self._stream()), "tc_set_camera_params")
-            torch.cuda.current_stream(self.device).synchronize()  # the temporaries die here
+            _lib.check(self._L.tc_set_camera_params_host(self._h, _ptr(cam), _ptr(th), C.c_void_p(rows.ctypes.data), self._stream()),
+                       "tc_set_camera_params")
+            self._param_staging = (car, cam, th)   # alive until the next upload: the copies above are stream-ordered
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -480,6 +484,12 @@ class TinyCarloVecEnv:
         d = dict(zip(keys, (int(v) for v in out)))
         d["blocks_per_sm"], d["track_per_thread"] = d["track_per_thread"] >> 4, d["track_per_thread"] & 1
         return d
+
+    def cull_stats(self) -> Dict[str, float]:
+        """Visible-set table bookkeeping: host builds, cache hits, milliseconds of the last / of all builds."""
+        out = (C.c_double * 4)()
+        _lib.check(self._L.tc_debug_cull_stats(self._h, out), "tc_debug_cull_stats")
+        return {"builds": int(out[0]), "cache_hits": int(out[1]), "last_build_ms": out[2], "total_build_ms": out[3]}
 
     @property
     def launch_count(self) -> int:
