@@ -542,18 +542,26 @@ def main():
                 traffic = ent["dram_bytes_per_env"] * N
     except Exception:
         pass
-    kernel_names = {1: "tc_render_env_banded_kernel<RGB>", 2: "tc_render_env_kernel<256,U8>", 3: "tc_render_classes_kernel<256,U8>",
-                    4: "tc_render_classes_kernel<256,U8>"}
+    def kernel_name(b):
+        """the render kernel a handle launches (tc_debug_render_info)"""
+        ri = b.render_info()
+        fmt = {"rgb": "RGB", "classes_bits": "BITS", "classes_bf16": "BF16"}.get(b.observation_space_format, "U8")
+        if ri["block_per_env"]:
+            return f"tc_render_envs_kernel<256,{fmt},{ri['envs_per_block']}>" if ri["envs_per_block"] else f"tc_render_env_kernel<256,{fmt}>"
+        if fmt in ("RGB", "BITS") and ri["banded_smem"]:
+            return "tc_prims_kernel + tc_draw_class_kernel<BITS>" if fmt == "BITS" else "tc_render_env_banded_kernel<RGB>"
+        return f"tc_render_classes_kernel<256,{fmt}>"
     if grouped:
+        for r, b in zip(group_rows, bases):
+            r["achieved_gbs"] = r["obs_bytes"] / (r["render_ms"] * 1e-3) / 1e9 if r["render_ms"] > 0 else 0.0
+            r["kernel"] = kernel_name(b)
         top = max(group_rows, key=lambda r: r["render_ms"])
         raster_ms, alg_bytes = top["render_ms"], top["obs_bytes"]
-        kname = ("tc_render_classes_kernel<256,U8>" if 5 * top["res"][0] * top["res"][1] > 128 * 1024 else "tc_render_env_kernel<256,U8>") + f" ({top['res'][0]}x{top['res'][1]} group)"
-        for r in group_rows:
-            r["achieved_gbs"] = r["obs_bytes"] / (r["render_ms"] * 1e-3) / 1e9 if r["render_ms"] > 0 else 0.0
+        kname = top["kernel"] + f" ({top['res'][0]}x{top['res'][1]} group)"
     else:
         raster_ms = kern["project"] + kern["raster"] if kern.get("project", 0) > 0.01 * max(kern["raster"], 1e-9) else kern["raster"]
         alg_bytes = bases[0].obs.numel() * bases[0].obs.element_size()
-        kname = kernel_names[args.config]
+        kname = kernel_name(bases[0])
     achieved = alg_bytes / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes, "kernel": kname, "kernel_ms_per_launch": raster_ms,

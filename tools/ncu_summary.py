@@ -13,7 +13,12 @@ def launches(path):
     hdr = rows[0]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg = OrderedDict()
-    for r in rows[1:]:
+    body = rows[1:]
+    first = next((i for i, r in enumerate(body) if r[ki].lstrip("void ").startswith("tc_")), 0)
+    if first:   # launches before the library's first kernel are torch's zero-fills of the freshly allocated tensors: not part of a step
+        print(f"# skipping {first} launches of the set-up (tensor allocation fills) before the first tc_* kernel")
+        body = body[first:]
+    for r in body:
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)   # -> us
         agg.setdefault(r[ki], []).append(v)

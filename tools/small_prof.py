@@ -1,9 +1,9 @@
 """A few steps of a small-frame config for ncu: usage small_prof.py [map] [H] [W] [N]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import torch
-from pair_util import make_config
+from tinycarlo_b200.config import make_config
 from tinycarlo_b200 import TinyCarloVecEnv
 MAP = sys.argv[1] if len(sys.argv) > 1 else "simple_layout"
 RES = [int(sys.argv[2]), int(sys.argv[3])] if len(sys.argv) > 3 else [84, 84]
