@@ -112,10 +112,18 @@ def port_arm(w, n_envs, steps, warmup, threads, min_seconds=0.0):
     workload. Runs `steps` lockstep passes, and keeps going until min_seconds have passed. -> (env-steps/s, seconds, passes).
     This is the only place besides tests/ and smoke() that executes oracle/ - as a measured baseline, never as the product."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import oracle as orc
-    from pair_util import oracle_env
-    from tinycarlo_b200.config import make_config
+    from tinycarlo_b200.config import make_config   # a plain dict builder: nothing of the CUDA path is touched in this arm
+
+    def oracle_env(cfg, n, wrapped=False, cam_rows=None, car_rows=None):
+        omap = orc.load_named_map(cfg["map"]["map_name"], cfg["map"]["pixel_per_meter"], cfg["map"].get("spawn_points"))
+        cc = cfg["camera"]
+        H, W = cc["resolution"]
+        if cam_rows is None:
+            cam_rows = orc.pack_cam(*orc.camera_matrices(cc["position"], cc["orientation"], cc["fov"], [H, W]), cc["max_range"])
+        if car_rows is None:
+            car_rows = orc.pack_car(cfg["car"], cfg["sim"].get("fps", 30))
+        return orc.OracleVecEnv(omap, n, car_rows, cam_rows, cc["line_thickness"], H, W, cfg["sim"]["observation_space_format"], wrapped=wrapped)
     reses = [w["res"]] if w["res"] else w["groups"]
     n_each = max(n_envs // len(reses), 1)
     envs, rngs = [], []

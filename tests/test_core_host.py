@@ -89,6 +89,7 @@ def test_host_core_replays_reference_trace(name):
 
 @pytest.mark.parametrize("H,W,spread,n,nlanes", [(24, 32, 12, 4000, 1), (24, 32, 12, 3000, 32), (24, 32, 12, 3000, -1), (48, 64, 300, 2500, -1),
                                                   (480, 640, 200, 120, -1), (48, 64, 300, 2500, 32),
+                                                  (24, 32, 12, 6000, -2), (48, 64, 300, 4000, -2), (84, 84, 40, 3000, -2), (480, 640, 200, 200, -2), (128, 160, 2000, 3000, -2),
                                                   (84, 84, 40, 1500, 32), (480, 640, 200, 120, 32)])
 def test_bitplane_rasteriser_vs_cv2(H, W, spread, n, nlanes):
     rng = np.random.default_rng(H * 7 + W + nlanes)
@@ -117,7 +118,7 @@ def test_bitplane_rasteriser_far_endpoints(mag):
             p0, p1 = p1, p0
         a = np.zeros((H, W), np.uint8)
         cv2.polylines(a, np.int32([[p0, p1]]), False, 255, t)
-        if not np.array_equal(a, polyline(H, W, p0, p1, t, nlanes=32)):
+        if not np.array_equal(a, polyline(H, W, p0, p1, t, nlanes=32)) or not np.array_equal(a, polyline(H, W, p0, p1, t, nlanes=-2)):
             bad.append((p0, p1, t))
     assert not bad, bad[:5]
     for t in (1, 2, 3):

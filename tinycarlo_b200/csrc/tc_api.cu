@@ -80,6 +80,7 @@ struct TcHandle {
     size_t track_smem = 0, proj_smem = 0, render_smem = 0;
     int max_edges = 0, plane_words_full = 0;
     int stagger_ns = 0, n_sms = 148;
+    int track_group = 32;       // lanes per env of tc_track_kernel (32 or 8)
     int track_per_thread = 1;   // tc_track_thread_kernel (one thread per env) instead of tc_track_kernel (a warp per env)
     long long *timeline = nullptr;
     bool fused_ok = false;
@@ -432,15 +433,20 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     }
 #undef TC_PREP_RENDER
     TC_TRYH(tc_install_cull(h, -1.0));   // the whole graph until the camera parameters are known (after the kernels' attributes: it asks for occupancies)
-    TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TC_CUDAH(cudaFuncSetAttribute(tc_track_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_classes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TC_CUDAH(cudaFuncSetAttribute(tc_raster_rgb_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    TC_CUDAH(tc_allow_max_smem(tc_track_kernel));
+    TC_CUDAH(tc_allow_max_smem(tc_track_kernel<32>));
+    TC_CUDAH(tc_allow_max_smem(tc_track_kernel<8>));
     TC_CUDAH(tc_allow_max_smem(tc_track_thread_kernel));
     TC_CUDAH(cudaFuncSetAttribute(tc_track_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // a warp per env pays off only when there are too few envs to fill the SMs with one thread each (TC_TRACK_MODE=warp|thread overrides)
     h->track_per_thread = num_envs >= 8192 ? 1 : 0;   // measured: 4096 envs 0.045 (warp) vs 0.062 ms (thread), 32768 envs 0.187 vs 0.044 ms
     if (const char *tm = getenv("TC_TRACK_MODE")) h->track_per_thread = (tm[0] == 't' || tm[0] == '1') ? 1 : 0;
+    // below that: 8 lanes per env once a warp per env would need more than one wave of warps (3 blocks x 8 warps per SM), else a warp per env
+    h->track_group = num_envs > 3 * 8 * h->n_sms / 2 ? 8 : 32;
+    if (const char *tg = getenv("TC_TRACK_GROUP")) h->track_group = atoi(tg) == 8 ? 8 : 32;
     TC_CUDAH(tc_allow_max_smem(tc_project_kernel));
     TC_CUDAH(tc_allow_max_smem(tc_raster_classes_kernel));
     TC_CUDAH(tc_allow_max_smem(tc_raster_rgb_kernel));
@@ -580,10 +586,9 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
         // envs with more segments than the primitive buffer holds are flagged and rendered by the banded kernel below
         if (!h->prims.prims) {
             TC_TRY(tc_dev_alloc(h, &h->prims.prims, (size_t)N * TC_PRIMS_CAP * TC_PRIMS_SEG_WORDS));
-            TC_TRY(tc_dev_alloc(h, &h->prims.tags, (size_t)N * TC_PRIMS_CAP));
-            TC_TRY(tc_dev_alloc(h, &h->prims.count, (size_t)N));
+            TC_TRY(tc_dev_alloc(h, &h->prims.cls_info, (size_t)N * C));
             TC_TRY(tc_dev_alloc(h, &h->prims.overflow, (size_t)N));
-            TC_CUDA(cudaMemsetAsync(h->prims.count, 0, (size_t)N * 4, st));
+            TC_CUDA(cudaMemsetAsync(h->prims.cls_info, 0, (size_t)N * C * 4, st));
             TC_CUDA(cudaMemsetAsync(h->prims.overflow, 0, (size_t)N, st));
         }
         TcRenderEnvArgs ea;
@@ -602,7 +607,7 @@ static int tc_launch_render(TcHandle *h, const uint8_t *mask, uint8_t *obs, int 
         TC_CUDA(cudaGetLastError());
         TcDrawArgs da;
         da.n_envs = N; da.n_classes = C; da.H = h->H; da.W = h->W; da.plane_words = h->plane_words_full; da.mask = mask; da.in = h->prims; da.obs = obs;
-        tc_draw_class_kernel<256, TC_FMT_BITS><<<N * C, 256, (size_t)h->plane_words_full * 4, st>>>(da);
+        tc_draw_class_kernel<256, TC_FMT_BITS><<<N * C, 256, ((size_t)h->plane_words_full * 4 + 15) & ~(size_t)15, st>>>(da);
         h->launches++;
         TC_CUDA(cudaGetLastError());
         ea.mask = h->prims.overflow; ea.obs = obs;   // (the flag is only set for envs the caller's mask selected)
@@ -687,9 +692,12 @@ static int tc_launch_track(TcHandle *h, int mode, const float *cc, const int32_t
     if (outs) ta.out = *outs;
     if (h->track_per_thread) {
         tc_track_thread_kernel<<<(h->n_envs + TC_TRACK1_THREADS - 1) / TC_TRACK1_THREADS, TC_TRACK1_THREADS, h->track_smem, st>>>(ta);
+    } else if (h->track_group == 8) {
+        const int envs_per_block = TC_TRACK_THREADS / 8;
+        tc_track_kernel<8><<<(h->n_envs + envs_per_block - 1) / envs_per_block, TC_TRACK_THREADS, h->track_smem, st>>>(ta);
     } else {
         const int envs_per_block = TC_TRACK_THREADS / 32;
-        tc_track_kernel<<<(h->n_envs + envs_per_block - 1) / envs_per_block, TC_TRACK_THREADS, h->track_smem, st>>>(ta);
+        tc_track_kernel<32><<<(h->n_envs + envs_per_block - 1) / envs_per_block, TC_TRACK_THREADS, h->track_smem, st>>>(ta);
     }
     h->launches++;
     TC_CUDA(cudaGetLastError());
@@ -835,7 +843,7 @@ int tc_debug_render_info(TcHandle *h, int32_t *out8) {
     if (!h || !out8) return tc_fail(TC_ERR_INVALID, "tc_debug_render_info: null argument");
     out8[0] = h->fused_all; out8[1] = h->fused_all ? h->env_pack : 0; out8[2] = h->env_chunks;
     out8[3] = (int32_t)(h->fused_all ? (h->env_pack ? h->envs_smem : h->env_smem) : h->render_smem);
-    out8[4] = h->track_per_thread + 16 * h->env_blocks; out8[5] = (int32_t)h->envb_smem; out8[6] = h->env_np; out8[7] = h->env_max_bytes;
+    out8[4] = h->track_per_thread + 16 * h->env_blocks + 1024 * h->track_group; out8[5] = (int32_t)h->envb_smem; out8[6] = h->env_np; out8[7] = h->env_max_bytes;
     return TC_OK;
 }
 

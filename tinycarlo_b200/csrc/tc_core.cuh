@@ -34,10 +34,15 @@ struct TcLanes {
 // (layer.py:44 `d.index(min(d))`).
 TC_HD void tc_group_argmin(const TcLanes &g, double &d, int &idx) {
 #if defined(__CUDA_ARCH__)
-    if (g.n == 1) return;   // a single-lane group (thread-per-env tracking): the lane's own result is the group's
-    for (int off = 16; off > 0; off >>= 1) {
-        double od = __shfl_xor_sync(0xffffffffu, d, off);
-        int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    // groups are aligned power-of-two slices of a warp (32: warp-per-env tracking; 8: four envs per warp; 1: thread-per-env, where
+    // the lane's own result is the group's): the xor butterfly below stays inside the slice
+    unsigned lane_in_warp;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane_in_warp));
+    // only the group's own lanes take part: the groups of a warp follow different control flow (one env scans, its neighbour does not)
+    const unsigned mask = g.n >= 32 ? 0xffffffffu : (((1u << g.n) - 1u) << (lane_in_warp & ~(unsigned)(g.n - 1)));
+    for (int off = g.n >> 1; off > 0; off >>= 1) {
+        double od = __shfl_xor_sync(mask, d, off);
+        int oi = __shfl_xor_sync(mask, idx, off);
         if (oi >= 0 && (idx < 0 || od < d || (od == d && oi < idx))) {
             d = od;
             idx = oi;
@@ -869,6 +874,24 @@ TC_HD void tc_setup_fill_convex_poly4(int W, int H, const int64_t (*v)[2], int r
     // the two scan-line walkers (kept in scalars: e?0 walks the vertices upwards, e?1 downwards)
     int idxA = imin, idxB = imin, yeA = y, yeB = y;
     int64_t xA = -TC_XY_ONE, xB = -TC_XY_ONE, dxA = 0, dxB = 0;
+    // A walker picks a polygon edge up on the scan line of the edge's start vertex (y == its rounded y: the loop below only stops
+    // on vertex rows), and only edges that lead to a LATER row, so the slope it computes there is a function of the edge alone:
+    // trunc(((xe - xs) * 2 + dy) / (2 * dy)), dy = the edge's rounded height in its downward direction. The block-per-env kernels
+    // (COMPACT) compute the four slopes up front - four independent divisions the hardware overlaps - instead of one after the
+    // other inside the data-dependent walk; the values, and therefore the spans, are the same (tests/test_core_host.py fuzzes both
+    // formulations against the oracle).
+    int64_t sl0 = 0, sl1 = 0, sl2 = 0, sl3 = 0;
+    if (COMPACT) {
+        const int ry0 = (int)((vy0 + delta) >> TC_XY_SHIFT), ry1 = (int)((vy1 + delta) >> TC_XY_SHIFT), ry2 = (int)((vy2 + delta) >> TC_XY_SHIFT),
+                  ry3 = (int)((vy3 + delta) >> TC_XY_SHIFT);
+#define TC_SLOPE(XA, RA, XB, RB) ((RB) == (RA) ? (int64_t)0 : ((RB) > (RA) ? tc_div_trunc(((XB) - (XA)) * 2 + ((RB) - (RA)), 2 * ((RB) - (RA))) \
+                                                                        : tc_div_trunc(((XA) - (XB)) * 2 + ((RA) - (RB)), 2 * ((RA) - (RB)))))
+        sl0 = TC_SLOPE(vx0, ry0, vx1, ry1);   // polygon edge k joins vertices k and k+1
+        sl1 = TC_SLOPE(vx1, ry1, vx2, ry2);
+        sl2 = TC_SLOPE(vx2, ry2, vx3, ry3);
+        sl3 = TC_SLOPE(vx3, ry3, vx0, ry0);
+#undef TC_SLOPE
+    }
     while (true) {
 #define TC_WALK(IDX, YE, X, DX, DI)                                                        \
         if (y >= YE) {                                                                     \
@@ -880,7 +903,9 @@ TC_HD void tc_setup_fill_convex_poly4(int W, int H, const int64_t (*v)[2], int r
                 if (ty > y) {                                                              \
                     int64_t xs = tc_sel4(idx0, vx0, vx1, vx2, vx3), xe = tc_sel4(idx, vx0, vx1, vx2, vx3); \
                     YE = ty;                                                               \
-                    DX = tc_div_trunc((xe - xs) * 2 + (ty - y), 2 * (ty - y));             \
+                    /* the polygon edge between idx0 and idx: the one with the smaller index, or edge 3 for the pair (3, 0) */ \
+                    DX = COMPACT ? tc_sel4(DI == 1 ? idx0 : idx, sl0, sl1, sl2, sl3)      \
+                                 : tc_div_trunc((xe - xs) * 2 + (ty - y), 2 * (ty - y));  \
                     X = xs;                                                                \
                     IDX = idx;                                                             \
                     break;                                                                 \

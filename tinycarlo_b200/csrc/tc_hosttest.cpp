@@ -162,7 +162,11 @@ HT_API void ht_polyline(uint8_t *img, int H, int W, int32_t x0, int32_t y0, int3
         // the fused kernel's split: every role sets up its own slots (as different warps do), then 32 lanes draw
         TcPrim prims[TC_MAX_PRIMS_PER_SEG];
         for (int i = 0; i < TC_MAX_PRIMS_PER_SEG; i++) prims[i].kind = TC_PRIM_NONE;
-        for (int role = 0; role < TC_N_ROLES; role++) tc_polyline_setup(W, H, x0, y0, x1, y1, thickness, role, prims);
+        // nlanes == -2: the block-per-env kernels' set-up variant (one code instance for the edge roles, walker slopes up front)
+        for (int role = 0; role < TC_N_ROLES; role++) {
+            if (nlanes == -2) tc_polyline_setup<true>(W, H, x0, y0, x1, y1, thickness, role, prims);
+            else tc_polyline_setup(W, H, x0, y0, x1, y1, thickness, role, prims);
+        }
         for (int lane = 0; lane < 32; lane++) {
             TcLanes g = {lane, 32};
             for (int i = 0; i < TC_MAX_PRIMS_PER_SEG; i++)

@@ -91,6 +91,10 @@ struct TcTrackArgs {
     TcOutputs out;
 };
 
+// G lanes per env (a power of two <= 32): the scalar part of a step is computed redundantly by the G lanes, the scans are spread
+// over them. 32 = a warp per env; 8 = four envs per warp, a quarter of the warps for the same envs - the better choice when a few
+// thousand envs cannot fill the SMs with one thread each (4096 envs: 1024 instead of 4096 warps, one wave instead of two).
+template <int G>
 __global__ void __launch_bounds__(TC_TRACK_THREADS, 3) tc_track_kernel(const TcTrackArgs a) {
     extern __shared__ __align__(128) unsigned char smem_blob[];
     __shared__ __align__(8) uint64_t bar;
@@ -103,9 +107,10 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS, 3) tc_track_kernel(const TcT
         tc_mbar_expect_tx(&bar, (uint32_t)a.layout.total_bytes);
         tc_bulk_g2s(smem_blob, a.blob, (uint32_t)a.layout.total_bytes, &bar);
     }
-    const int warp = threadIdx.x >> 5;
-    const int env = blockIdx.x * (TC_TRACK_THREADS / 32) + warp;
-    TcLanes g = {(int)(threadIdx.x & 31), 32};
+    const int env = blockIdx.x * (TC_TRACK_THREADS / G) + (int)threadIdx.x / G;
+    TcLanes g = {(int)(threadIdx.x & (G - 1)), G};
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));   // the lanes of this env's group
+    const int leader = (threadIdx.x & 31) & ~(G - 1);
     tc_mbar_wait(&bar, 0);
     if (env >= a.n_envs) return;
     TcTrackTables t = tc_track_tables(smem_blob, a.layout);
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS, 3) tc_track_kernel(const TcT
         // the action of this step is ignored; reward 0, not terminated, not truncated, empty info (env.py:101-113)
         int node = -1;
         if (g.lane == 0 && a.rng) node = tc_spawn_draw(t, a.rng + (size_t)env * TC_RNG_N, a.spawn_points, a.n_spawn_points);
-        node = __shfl_sync(0xffffffffu, node, 0);
+        node = __shfl_sync(gmask, node, leader);
         tc_load_state(sf, si, s);
         auto_reset = tc_car_reset(t, cp, s, node);
         if (auto_reset && g.lane == 0 && a.last_spawn) a.last_spawn[env] = node;
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(TC_TRACK_THREADS, 3) tc_track_kernel(const TcT
         if (a.spawn_nodes) node = a.spawn_nodes[env];
         else {
             if (g.lane == 0 && a.rng) node = tc_spawn_draw(t, a.rng + (size_t)env * TC_RNG_N, a.spawn_points, a.n_spawn_points);
-            node = __shfl_sync(0xffffffffu, node, 0);
+            node = __shfl_sync(gmask, node, leader);
         }
         if (!tc_car_reset(t, cp, s, node)) return;
         if (g.lane == 0 && a.last_spawn) a.last_spawn[env] = node;
@@ -1409,10 +1414,10 @@ __global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_render_envs_ker
 #define TC_PRIMS_CAP 64
 #define TC_PRIMS_SEG_WORDS (TC_MAX_PRIMS_PER_SEG * 8)
 struct TcPrimsOut {
-    int32_t *prims;   // [N][TC_PRIMS_CAP][12][8]
-    uint8_t *tags;    // [N][TC_PRIMS_CAP] class of each segment
-    int32_t *count;   // [N] segments (0 for masked-out envs; > TC_PRIMS_CAP: overflow, nothing else written)
-    uint8_t *overflow;// [N] 1: the env needs the fallback kernel
+    int32_t *prims;    // [N][TC_PRIMS_CAP][12][8], an env's segments sorted by class
+    int32_t *cls_info; // [N][C]: first segment << 8 | segments of (env, class); -1: the env overflowed. ONE load tells a draw block what to
+                       // do - its loads queue behind the observation stores of the co-resident blocks, so every dependent load costs thousands of cycles
+    uint8_t *overflow; // [N] 1: the env needs the fallback kernel
 };
 
 template <int NT, int E>
@@ -1426,14 +1431,17 @@ __global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_prims_kernel(co
     __shared__ TcCellBlob s_desc[E];
     __shared__ int4 s_seg[CAP];
     __shared__ uint16_t s_tag[CAP];   // env slot << 8 | class
-    __shared__ int s_gpos[CAP];       // index of the segment within its env
+    __shared__ int s_gpos[CAP];       // position of the segment in its env's class-sorted list
     __shared__ int s_task, s_nseg, s_ntask;
+    __shared__ int s_clscnt[E][TC_MAX_CLASSES], s_clsoff[E][TC_MAX_CLASSES];
 #define TC_REGION(e) (smem_raw + (size_t)(e) * a.region_bytes)
 #define TC_PW ((int32_t *)(smem_raw + (size_t)E * a.region_bytes))
+#define TC_RANK(e) ((uint16_t *)(TC_REGION(e) + (size_t)a.np * 24))   /* rank of a segment within its class: over the dead camera-pass scratch */
     if (threadIdx.x == 0) {
         tc_mbar_init(&bar, E);
         tc_fence_mbar_init();
     }
+    if (threadIdx.x < E * TC_MAX_CLASSES) (&s_clscnt[0][0])[threadIdx.x] = 0;
     __syncwarp();
     if (threadIdx.x < E) {
         const int e = threadIdx.x, env = blockIdx.x * E + e;
@@ -1467,16 +1475,28 @@ __global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_prims_kernel(co
             // masked-out envs keep their previous frame: the draw kernel skips them by the same mask, and the fallback kernel by a
             // cleared overflow flag
             const bool ovf = s_active[e] && seg_cnt[e] > TC_PRIMS_CAP;
-            if (s_active[e]) o.count[env] = seg_cnt[e];
             o.overflow[env] = ovf ? 1 : 0;
-            if (ovf) seg_cnt[e] = 0;   // rendered by the fallback kernel: no set-up here
+            if (ovf) { seg_cnt[e] = 0; s_active[e] = 2; }   // rendered by the fallback kernel: no set-up here
         }
     }
     __syncthreads();
+    // class-sorted order: a segment's rank among the env's segments of its class, then the classes' offsets
+    for (int e = 0; e < E; e++) {
+        const uint8_t *cls = (const uint8_t *)((const int4 *)TC_REGION(e) + s_desc[e].n_edges);
+        for (int i = threadIdx.x; i < seg_cnt[e]; i += NT) TC_RANK(e)[i] = (uint16_t)atomicAdd(&s_clscnt[e][cls[i]], 1);
+    }
     if (threadIdx.x == 0) {
         int acc = 0;
         for (int e = 0; e < E; e++) { s_pref[e] = acc; acc += seg_cnt[e]; }
         s_pref[E] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < E * a.n_classes) {
+        const int e = threadIdx.x / a.n_classes, c = threadIdx.x - e * a.n_classes, env = blockIdx.x * E + e;
+        int off = 0;
+        for (int k = 0; k < c; k++) off += s_clscnt[e][k];
+        s_clsoff[e][c] = off;
+        if (env < a.n_envs && s_active[e]) o.cls_info[(size_t)env * a.n_classes + c] = s_active[e] == 2 ? -1 : ((off << 8) | s_clscnt[e][c]);
     }
     __syncthreads();
     for (int base = 0; base < s_pref[E]; base += a.prim_chunks * TC_ENV_CHUNK) {
@@ -1495,8 +1515,7 @@ __global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_prims_kernel(co
                 const uint8_t cls = ((const uint8_t *)(segs + s_desc[e].n_edges))[i];
                 s_seg[threadIdx.x] = segs[i];
                 s_tag[threadIdx.x] = (uint16_t)((e << 8) | cls);
-                s_gpos[threadIdx.x] = i;
-                o.tags[(size_t)(blockIdx.x * E + e) * TC_PRIMS_CAP + i] = cls;
+                s_gpos[threadIdx.x] = s_clsoff[e][cls] + TC_RANK(e)[i];
             }
             if (threadIdx.x == 0) {
                 s_task = 0; s_nseg = nseg;
@@ -1527,6 +1546,7 @@ __global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_prims_kernel(co
     }
 #undef TC_REGION
 #undef TC_PW
+#undef TC_RANK
 }
 
 struct TcDrawArgs {
@@ -1541,18 +1561,12 @@ struct TcDrawArgs {
 template <int NT, int FMT>
 __global__ void __launch_bounds__(NT) tc_draw_class_kernel(const TcDrawArgs a) {
     extern __shared__ __align__(128) uint32_t plane[];
-    __shared__ int s_list[TC_PRIMS_CAP];   // this class's segments
-    __shared__ int s_n;
     const int env = blockIdx.x / a.n_classes, c = blockIdx.x - env * a.n_classes;
+    const int info = a.in.cls_info[blockIdx.x];   // issued before the mask test: one round trip for both
     if (a.mask && !a.mask[env]) return;
-    if (a.in.overflow[env]) return;        // the fallback kernel renders this env
+    if (info < 0) return;                  // the env overflowed the primitive buffer: the fallback kernel renders it
     const int tid = threadIdx.x, lane = tid & 31;
-    const int cnt = a.in.count[env];
-    if (tid == 0) s_n = 0;
-    __syncthreads();
-    if (tid < cnt && a.in.tags[(size_t)env * TC_PRIMS_CAP + tid] == c) s_list[atomicAdd(&s_n, 1)] = tid;
-    __syncthreads();
-    const int n = s_n;
+    const int n = info & 0xff, first = info >> 8;
     const size_t frame_words = ((size_t)a.H * a.W + 31) / 32;
     uint32_t *out = (uint32_t *)a.obs + ((size_t)env * a.n_classes + c) * frame_words;
     if (n == 0) {   // nothing of this class in view: the plane is zeros
@@ -1563,8 +1577,6 @@ __global__ void __launch_bounds__(NT) tc_draw_class_kernel(const TcDrawArgs a) {
             for (size_t i = tid; i < frame_words; i += NT) out[i] = 0u;
         return;
     }
-    for (int i = tid; i < a.plane_words; i += NT) plane[i] = 0;
-    __syncthreads();
     const TcPlane pl = {plane, a.H, a.W, 0, a.H, 0};
     const TcLanes g = {lane, 32}, g1 = {0, 1};
     const int32_t *base = a.in.prims + (size_t)env * TC_PRIMS_CAP * TC_PRIMS_SEG_WORDS;
@@ -1575,14 +1587,16 @@ __global__ void __launch_bounds__(NT) tc_draw_class_kernel(const TcDrawArgs a) {
         const int p = r * NT + lane * (NT / 32) + (tid >> 5);
         TcPrim q;
         q.kind = TC_PRIM_NONE;
-        if (p < n * TC_MAX_PRIMS_PER_SEG) {
-            const int4 *src = (const int4 *)(base + (size_t)s_list[p / TC_MAX_PRIMS_PER_SEG] * TC_PRIMS_SEG_WORDS + (p % TC_MAX_PRIMS_PER_SEG) * 8);
-            const int4 lo = src[0];
+        if (p < n * TC_MAX_PRIMS_PER_SEG) {   // both halves at once: the loads are in flight while the plane is zeroed
+            const int4 *src = (const int4 *)(base + (size_t)(first + p / TC_MAX_PRIMS_PER_SEG) * TC_PRIMS_SEG_WORDS + (p % TC_MAX_PRIMS_PER_SEG) * 8);
+            const int4 lo = src[0], hi = src[1];
             q.kind = lo.x; q.a[0] = lo.y; q.a[1] = lo.z; q.a[2] = lo.w;
-            if (q.kind != TC_PRIM_NONE) {
-                const int4 hi = src[1];
-                q.a[3] = hi.x; q.a[4] = hi.y; q.a[5] = hi.z; q.a[6] = hi.w;
-            }
+            q.a[3] = hi.x; q.a[4] = hi.y; q.a[5] = hi.z; q.a[6] = hi.w;
+        }
+        if (r == 0) {
+            uint4 *p4 = (uint4 *)plane;
+            for (int i = tid; i < (a.plane_words + 3) / 4; i += NT) p4[i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
         }
         const int items = q.kind != TC_PRIM_NONE ? tc_prim_items(q) : 0;
         unsigned big = __ballot_sync(0xffffffffu, items > TC_SMALL_PRIM_ITEMS);

@@ -482,7 +482,8 @@ class TinyCarloVecEnv:
         _lib.check(self._L.tc_debug_render_info(self._h, out), "tc_debug_render_info")
         keys = ("block_per_env", "envs_per_block", "prim_chunks", "render_smem", "track_per_thread", "banded_smem", "cell_nodes_cap", "cell_bytes_cap")
         d = dict(zip(keys, (int(v) for v in out)))
-        d["blocks_per_sm"], d["track_per_thread"] = d["track_per_thread"] >> 4, d["track_per_thread"] & 1
+        v = d["track_per_thread"]
+        d["track_per_thread"], d["blocks_per_sm"], d["track_lanes_per_env"] = v & 1, (v >> 4) & 63, 1 if v & 1 else v >> 10
         return d
 
     def cull_stats(self) -> Dict[str, float]:

@@ -3,6 +3,7 @@ Usage: python tools/parity_soak.py [n_envs] [steps] [H] [W] [map]"""
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+FMT = os.environ.get("TC_FMT", "classes")   # classes | classes_bits (decoded and compared with the same oracle frames)
 import numpy as np, torch
 from pair_util import make_config, oracle_env, stanley_actions
 from tinycarlo_b200 import TinyCarloVecEnv
@@ -13,7 +14,16 @@ H = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 W = int(sys.argv[4]) if len(sys.argv) > 4 else 160
 mp = sys.argv[5] if len(sys.argv) > 5 else "knuffingen"
 cfg = make_config(mp, "classes", cam={"resolution": [H, W]}, car={"max_velocity": 0.15} if mp == "simple_layout" else None)
-env = TinyCarloVecEnv(cfg, n, device="cuda:0")
+env = TinyCarloVecEnv(cfg, n, device="cuda:0", obs_format=FMT)
+FIELDS = ["cte", "heading_error", "velocity", "reward"] + [f"dist_{c}" for c in env.class_names]
+per_field = {f: {"max_abs": 0.0, "max_rel": 0.0} for f in FIELDS}
+
+
+def frames():
+    o = env.obs.cpu().numpy()
+    if FMT == "classes_bits":
+        return np.unpackbits(o.view(np.uint32).view(np.uint8), axis=-1, bitorder="little")[..., : H * W].reshape(n, -1, H, W) * 255
+    return o
 oenv = oracle_env(cfg, n)
 rng = np.random.default_rng(12345)
 env.reset(seed=2024)
@@ -31,7 +41,7 @@ for t in range(steps):
         cc[rng.random(n) < 0.05, 0] = -0.8
     env.step({"car_control": torch.from_numpy(cc).cuda(), "maneuver": torch.from_numpy(man).cuda()})
     oenv.step(cc.astype(np.float64), man)
-    obs = env.obs.cpu().numpy()
+    obs = frames()
     d = obs != oenv.obs
     bf = d.reshape(n, -1).any(axis=1)
     st["bad_frames"] += int(bf.sum()); st["bad_pixels"] += int(d.sum())
@@ -44,13 +54,23 @@ for t in range(steps):
     i64 = env.out["info_f64"].cpu().numpy()
     den = np.maximum(np.abs(oenv.info), 1e-6)
     st["max_rel_info"] = max(st["max_rel_info"], float((np.abs(i64 - oenv.info) / den).max()))
+    for k, f in enumerate(FIELDS):   # per field: absolute error, and relative error where the value is not (almost) zero
+        ad = np.abs(i64[:, k] - oenv.info[:, k])
+        per_field[f]["max_abs"] = max(per_field[f]["max_abs"], float(ad.max()))
+        big = np.abs(oenv.info[:, k]) > 1e-3
+        if big.any():
+            per_field[f]["max_rel"] = max(per_field[f]["max_rel"], float((ad[big] / np.abs(oenv.info[big, k])).max()))
     st["env_steps"] += n
     done = (oenv.terminated | oenv.truncated).astype(bool)
     if done.any():
         env.reset_done()
         oenv.reset(env._spawn_nodes.cpu().numpy(), mask=done)
         st["resets"] += int(done.sum())
-        st["bad_frames"] += int((env.obs.cpu().numpy() != oenv.obs).reshape(n, -1).any(axis=1).sum())
+        st["bad_frames"] += int((frames() != oenv.obs).reshape(n, -1).any(axis=1).sum())
 st["seconds"] = round(time.time() - t0, 1)
+st["info_error_per_field"] = per_field
+st["max_rel_info_note"] = "max over all info fields of |gpu - oracle| / max(|oracle|, 1e-6): dominated by values near zero (see info_error_per_field: max_abs, and max_rel over |value| > 1e-3)"
+st["kernels"] = env.render_info()
+st["obs_format"] = FMT
 st["config"] = f"{mp} {H}x{W} classes, {n} envs x {steps} steps, Stanley + noise, maneuver changes every 25 steps, 5% reverse bursts"
 print(json.dumps(st))
