@@ -204,7 +204,7 @@ static int tc_install_cull(TcHandle *h, double radius) {
     if (!cull.blob.empty()) TC_CUDA(cudaMemcpy(c.d_blob, cull.blob.data(), cull.blob.size(), cudaMemcpyHostToDevice));
     {
         // The packed small-frame kernel (tc_render_envs_kernel, 3 blocks of 256 threads per SM): E envs per block and 1 or 2
-        // 32-segment chunks of primitive slots, chosen for the most envs in flight per SM without dropping below 2 blocks per SM
+        // 32-segment chunks of primitive slots, chosen for the most envs in flight per SM without dropping below 3 blocks per SM
         // (fewer blocks hide the latency-bound phases worse than fuller lanes gain); E = 1 never beats tc_render_env_kernel
         // (measured), which stays the fallback. TC_ENV_PACK=0|2|4 and TC_ENV_CHUNKS=1|2 override.
         int pack = 0, chunks = 1, nblocks = 0;
@@ -218,7 +218,8 @@ static int tc_install_cull(TcHandle *h, double radius) {
                     cudaError_t oe = ee == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tc_render_envs_kernel<256, TC_FMT_U8, 2>, 256, sm)
                                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tc_render_envs_kernel<256, TC_FMT_U8, 4>, 256, sm);
                     if (oe != cudaSuccess) { cudaGetLastError(); continue; }
-                    if (blocks >= (ee == 2 ? 2 : 3) && ee * blocks > best) { best = ee * blocks; pack = ee; chunks = cc; nblocks = blocks; }
+                    // (at 2 blocks per SM the packed kernel loses to the one-env kernel at 4: config 5's wide cameras, 0.42 vs 0.35 ms)
+                    if (blocks >= 3 && ee * blocks > best) { best = ee * blocks; pack = ee; chunks = cc; nblocks = blocks; }
                 }
             if (const char *pe = getenv("TC_ENV_PACK")) {
                 const int v = atoi(pe);

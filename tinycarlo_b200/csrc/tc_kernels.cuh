@@ -485,6 +485,9 @@ __device__ __forceinline__ void tc_store_plane(uint8_t *out, size_t nbytes, cons
 
 // The same for the block-per-env kernels, whose time goes into instructions rather than into the stores: a frame is mostly
 // background, so the 0x00/0xFF expansion is skipped for the (97 % of) vectors whose 16 plane bits are all clear.
+// (Tried in round 2 and rejected: for aligned output, four half-word loads per thread and a warp ballot that writes 4 x 32 background
+// vectors at once - the store phase falls from 37 % to ~12 % of the packed kernel's instructions, but the bursts of back-to-back
+// stores made every small-frame configuration 3-4 % SLOWER: the per-vector work paces the stores.)
 template <int NT>
 __device__ __forceinline__ void tc_store_plane_sparse(uint8_t *out, size_t nbytes, const uint32_t *plane, bool any) {
     const int tid = threadIdx.x;
