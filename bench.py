@@ -35,6 +35,7 @@ import numpy as np  # noqa: E402
 import workloads as WL  # noqa: E402  (baseline/workloads.py: plain data, no product / oracle imports)
 
 UNIT = "env-steps/s"
+SETUP = {}   # one-time set-up costs worth reporting (config 5: per-env camera parameters and their visible-set tables)
 
 
 def host_threads():
@@ -252,11 +253,16 @@ def build_env(w, N, dev, rank, world):
         env = TinyCarloGroupedVecEnv(cfg, list(zip(sizes, w["groups"])), device=dev, group_index_offsets=offs, autoreset="next_step")
         p = WL.config5_params(total)
         ms = []
+        t0 = time.perf_counter()
         for e, n, o in zip(env.envs, sizes, offs):
             sl = slice(o, o + n)
             e.set_camera_params(position=p["position"][sl], orientation=p["orientation"][sl], fov=p["fov"][sl])
             e.set_car_params(**{k: v[sl] for k, v in p["car"].items()})
             ms.append(torch.from_numpy(p["car"]["max_steering_angle"][sl]).to(dev, torch.float32))
+        # one-time cost of per-env camera parameters: E / K of every env on the host (the reference's cv2.Rodrigues / numpy calls,
+        # for bit parity) plus the visible-set tables of each group, built once per camera reach and cached by the library
+        SETUP["set_params_s"] = time.perf_counter() - t0
+        SETUP["visible_set_tables"] = [e.cull_stats() for e in env.envs]
         return env, env.envs, torch.cat(ms)
     cfg = make_config(w["map"], w["fmt"], car=w["car"], cam={"resolution": w["res"]})
     base = TinyCarloVecEnv(cfg, N, device=dev, env_index_offset=rank * N, autoreset="next_step")
@@ -596,7 +602,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_dict(w, args, world), "obs_gbs": value / (N * world) * obs_b * world / 1e9,
             "sustained": sustained, "cuda_graph": graph, "clocks": clocks, "e2e": e2e, "e2e_obs_to_host": e2e_obs, "gpu_launches": n_launch,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_baseline_port": cpu_port, "library": {"so_hash": so_hash},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_baseline_port": cpu_port, "library": {"so_hash": so_hash}, "setup": SETUP or None,
             "episode_stats": {"finished": st[0], "truncated": st[1], "reward_sum": st[2], "env_steps": st[3]}}
     print(json.dumps(line), flush=True)
     if world > 1:
