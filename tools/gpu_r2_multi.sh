@@ -13,4 +13,4 @@ except Exception as e:
 PY
 }
 nvidia-smi -L | wc -l
-run 2 5; run 4 5; run 8 5; run 8 4; run 8 3; run 1 5
+run 2 5; run 4 5; run 8 5; run 8 4; run 8 2
