@@ -1041,7 +1041,10 @@ __host__ __device__ inline size_t tc_env_smem_bytes(size_t np, int max_bytes, in
 // classes as bytes behind them (segs + d.n_edges); the scratch arrays it used are dead afterwards. All threads call it.
 // NT threads (numbered tid = 0..NT-1) work on the env; the block barriers inside are hit by the whole block, so every thread of
 // the block must call it (the packed kernel runs one instance per env slot side by side, NT = its threads per env).
-template <int NT>
+// MERGED: the in-range flags of the range passes are taken inside the second near-plane pass instead of in a sweep of their own (one
+// barrier and one pass over the nodes less). Only for the kernels that run at 80 registers: in the 64-register kernels it costs 16
+// bytes of spills, and a spill there queues behind the observation stores.
+template <int NT, bool MERGED = false>
 __device__ __forceinline__ void tc_env_camera_pass(unsigned char *smem_raw, size_t np, const unsigned char *tab_smem, const TcCellBlob &d,
                                                uint64_t *bar, const double *pose, const double *cam, int H, int W, int *seg_cnt,
                                                const int tid = threadIdx.x, const uint32_t phase = 0 /* mbarrier parity; 0xffffffff: nothing to wait for */) {
@@ -1069,11 +1072,16 @@ __device__ __forceinline__ void tc_env_camera_pass(unsigned char *smem_raw, size
         const bool range = pass >= 2, outgoing = (pass & 1) == 0;
         const double tz = range ? -max_range : -0.0000001;
         uint8_t *src = range ? (outgoing ? rA : rB) : (outgoing ? fA : fB), *dst = range ? (outgoing ? rB : rA) : (outgoing ? fB : fA);
-        if (pass == 2) {
+        if (!MERGED && pass == 2) {
             for (int v = tid; v < n; v += NT) rA[v] = sc.Pz[v] > -max_range;
             __syncthreads();
         }
-        for (int v = tid; v < n; v += NT) dst[v] = src[v] | (uint8_t)tc_clip_pass_node(ct, sc, src, v, outgoing, tz);
+        for (int v = tid; v < n; v += NT) {
+            dst[v] = src[v] | (uint8_t)tc_clip_pass_node(ct, sc, src, v, outgoing, tz);
+            // the in-range flag of the range passes is taken on the z the near-plane passes leave behind (camera.py:80: depths is
+            // a live view); a node's z is final for that purpose once its own pass-1 move is done
+            if (MERGED && pass == 1) rA[v] = sc.Pz[v] > -max_range;
+        }
         __syncthreads();
     }
     for (int v = tid; v < n; v += NT) {
@@ -1304,7 +1312,7 @@ __global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_render_envs_ker
     // ---- camera pass (camera.py:52-110) of the E envs side by side: thread -> (env slot j, index of its TPE threads)
     {
         const int j = threadIdx.x / TPE;
-        tc_env_camera_pass<TPE>(TC_REGION(j), (size_t)a.np, TC_REGION(j) + tc_env_off_tables((size_t)a.np), s_desc[j], &bar, s_pose[j], s_cam[j], a.H, a.W,
+        tc_env_camera_pass<TPE, true>(TC_REGION(j), (size_t)a.np, TC_REGION(j) + tc_env_off_tables((size_t)a.np), s_desc[j], &bar, s_pose[j], s_cam[j], a.H, a.W,
                                 &seg_cnt[j], (int)threadIdx.x - j * TPE);
     }
     if (threadIdx.x == 0) {
@@ -1341,7 +1349,10 @@ __global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_render_envs_ker
             }
         }
         __syncthreads();
-        // set-up: (role, chunk) tasks from a queue, lane = segment of the chunk; spans (role 0) are handed out first
+        // set-up: (role, chunk) tasks from a queue, lane = segment of the chunk; spans (role 0) are handed out first.
+        // (Tried in round 2 and rejected: draw tasks in the same queue, each waiting only for the set-up task that fills its slot, so
+        // that the short roles' primitives are drawn while the spans are still being set up - no barrier between the phases, but
+        // 9-10 % slower on every small-frame configuration: the ticket order serialises what the barrier let all warps share.)
         while (true) {
             int k = 0;
             if ((threadIdx.x & 31) == 0) k = atomicAdd(&s_task, 1);
@@ -1469,7 +1480,7 @@ __global__ void __launch_bounds__(NT, TC_ENVS_MIN_BLOCKS(NT)) tc_prims_kernel(co
     __syncthreads();
     {
         const int j = threadIdx.x / TPE;
-        tc_env_camera_pass<TPE>(TC_REGION(j), (size_t)a.np, TC_REGION(j) + tc_env_off_tables((size_t)a.np), s_desc[j], &bar, s_pose[j], s_cam[j], a.H, a.W,
+        tc_env_camera_pass<TPE, true>(TC_REGION(j), (size_t)a.np, TC_REGION(j) + tc_env_off_tables((size_t)a.np), s_desc[j], &bar, s_pose[j], s_cam[j], a.H, a.W,
                                 &seg_cnt[j], (int)threadIdx.x - j * TPE);
     }
     if (threadIdx.x < E) {
