@@ -68,3 +68,53 @@ def test_two_rank_job_matches_single_process():
         g = r[4]
         assert g.shape == (2, 4)
         assert list(g[:, 0]) == [6, 5] and list(g[:, 1]) == [6, 5] and list(g[:, 2]) == [6.0, 10.0] and list(g[:, 3]) == [6, 5]
+
+
+def _worker_groups(rank, world, port, sizes, q):
+    """config 5's sharding on the host side: every rank takes a contiguous slice of EVERY resolution group; env seeds and per-env
+    parameters are functions of the global env index"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline"))
+    import workloads as WL
+    from tinycarlo_b200.distributed import shard_groups
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    local, offs = shard_groups(sizes, rank, world)
+    t = MapTables(resolve_map_path({"map_name": "knuffingen"}, None), 222, SPAWN_KNUFF)
+    p = WL.config5_params(sum(sizes))
+    draws, fov = [], []
+    for n, o in zip(local, offs):
+        draws.append(SpawnSampler(t, n, table_len=3, env_index_offset=o).seed(7))
+        fov.append(p["fov"][o:o + n])
+    counts = torch.tensor([float(sum(local))], dtype=torch.float64)
+    dist.all_reduce(counts)
+    q.put((rank, local, offs, draws, fov, float(counts.item())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_resolution_groups_match_single_process():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline"))
+    import workloads as WL
+    sizes, world = [7, 5, 9], 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_groups, args=(r, world, port, sizes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    t = MapTables(resolve_map_path({"map_name": "knuffingen"}, None), 222, SPAWN_KNUFF)
+    single = SpawnSampler(t, sum(sizes), table_len=3).seed(7)
+    fov = WL.config5_params(sum(sizes))["fov"]
+    base = np.cumsum([0] + sizes)
+    for g in range(len(sizes)):     # group g of the job = the ranks' slices of it, in rank order
+        got = np.concatenate([r[3][g] for r in res])
+        assert np.array_equal(got, single[base[g]:base[g + 1]]), g
+        assert np.array_equal(np.concatenate([r[4][g] for r in res]), fov[base[g]:base[g + 1]])
+    assert res[0][5] == sum(sizes) and [sum(r[1]) for r in res] == [11, 10]
