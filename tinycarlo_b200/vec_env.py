@@ -144,6 +144,10 @@ class TinyCarloVecEnv:
             if name == "obs" and not with_obs:
                 t = None
             setattr(o, name, None if t is None else t.data_ptr())
+        # what step() hands back is the same set of tensors every time: build the views and the info dict once (a step is two
+        # kernel launches; at a few thousand small frames the Python around them shows in the eager env-steps/s)
+        self._flag_views = (self.out["terminated"].view(torch.bool), self.out["truncated"].view(torch.bool))
+        self._info_cache = self._info()
         return o
 
     def _stream(self):
@@ -301,20 +305,22 @@ class TinyCarloVecEnv:
         if cc.device != self.device or man.device != self.device or cc.shape != (self.num_envs, 2) or man.shape != (self.num_envs,):
             raise ValueError("action tensors must live on the env's device with shapes [N,2] and [N]")
         outs = self._outs if not self.no_observation else self._outs_noobs
-        with torch.cuda.device(self.device):
-            if not self._was_reset:
-                raise _lib.TinyCarloError("call reset() before step()")
-            fn = self._L.tc_step_f64 if f64 else self._L.tc_step
-            dbg = self._debug and not torch.cuda.is_current_stream_capturing()
-            if dbg:
+        if not self._was_reset:
+            raise _lib.TinyCarloError("call reset() before step()")
+        fn = self._L.tc_step_f64 if f64 else self._L.tc_step
+        if self._debug and not torch.cuda.is_current_stream_capturing():
+            with torch.cuda.device(self.device):
                 self.profile_begin(1)
-            _lib.check(fn(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
-            if dbg:
+                _lib.check(fn(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
                 ms, _ = self.profile_end()
-                print(f"all: {ms['track'] + ms['project'] + ms['raster']:.3f} ms | obs render {ms['project'] + ms['raster']:.3f} ms | "
-                      f"car step + info {ms['track']:.3f} ms  ({self.num_envs} envs)")
-        o = self.out
-        return self.obs, o["reward"], o["terminated"].view(torch.bool), o["truncated"].view(torch.bool), self._info()
+            print(f"all: {ms['track'] + ms['project'] + ms['raster']:.3f} ms | obs render {ms['project'] + ms['raster']:.3f} ms | "
+                  f"car step + info {ms['track']:.3f} ms  ({self.num_envs} envs)")
+        elif torch.cuda.current_device() == self.device.index:   # the usual case: skip the device context manager (~10 us of Python)
+            _lib.check(fn(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
+        else:
+            with torch.cuda.device(self.device):
+                _lib.check(fn(self._h, _ptr(cc), _ptr(man), C.byref(outs), self._stream()), "tc_step")
+        return self.obs, self.out["reward"], self._flag_views[0], self._flag_views[1], dict(self._info_cache)
 
     def capture(self, policy_fn: Optional[Callable[["TinyCarloVecEnv"], Dict[str, torch.Tensor]]] = None, steps: int = 1,
                 warmup: int = 3) -> "torch.cuda.CUDAGraph":
