@@ -203,6 +203,11 @@ TC_API int tc_debug_set_timeline(TcHandle *h, long long *dev_timeline);
  * -2: this handle renders per class and has no such tables), number of cell descriptors, mean and maximum node count of a
  * cell. tc_set_camera_params rebuilds the tables (and synchronises the stream) when the cameras' reach changes. Setting
  * the environment variable TC_CULL=0 switches the culling off. */
+/* Episode statistics of one step in one launch (the numbers the ranks of a multi-GPU job all-gather over NCCL at log cadence):
+ * dev_acc4[0] += envs with terminated | truncated, [1] += truncated, [2] += sum of rewards, [3] += n. Works on any reward / flag
+ * tensors of the current device (the kernels' own outputs or what the reward / termination wrappers made of them). */
+TC_API int tc_episode_stats(const float *dev_reward, const uint8_t *dev_terminated, const uint8_t *dev_truncated, int32_t n, double *dev_acc4,
+                 void *stream);
 TC_API int tc_debug_cull_info(TcHandle *h, double *host_out4);
 /* Diagnostics: which kernels this handle launches. out8 = {block-per-env render path (0/1), envs per block of the packed
  * kernel (0: one-env kernel), its 32-segment chunks, dynamic shared memory of the render kernel, thread-per-env tracking (0/1),

@@ -474,3 +474,24 @@ def test_cuda_guard_bands_determinism_and_full_overwrite(case):
     for buf, nb in guards:
         assert bool((buf[:G] == 0x5C).all()) and bool((buf[G + nb + ((-nb) % 16):] == 0x5C).all()), "a kernel wrote outside an output buffer"
     env.close()
+
+
+def test_cuda_episode_stats_kernel_matches_torch():
+    """EpisodeStats.update on CUDA tensors is one launch of tc_episode_stats; it must count what the torch formulation counts
+    (bool and uint8 flags, sizes that are not multiples of the block, accumulation over calls)."""
+    from tinycarlo_b200.distributed import EpisodeStats
+    torch.manual_seed(0)
+    st = EpisodeStats(torch.device("cuda:0"))
+    want = torch.zeros(4, dtype=torch.float64)
+    for n, as_bool in ((1, True), (255, True), (4096, False), (100003, True)):
+        reward = torch.randn(n, device="cuda:0")
+        term = torch.rand(n, device="cuda:0") < 0.1
+        trunc = torch.rand(n, device="cuda:0") < 0.05
+        if not as_bool:
+            term, trunc = term.to(torch.uint8), trunc.to(torch.uint8)
+        st.update(reward, term, trunc)
+        want += torch.tensor([float((term.bool() | trunc.bool()).sum()), float(trunc.sum()), float(reward.double().sum()), float(n)], dtype=torch.float64)
+    got = st.local.cpu()
+    assert torch.equal(got[[0, 1, 3]], want[[0, 1, 3]]), (got, want)
+    assert abs(float(got[2] - want[2])) < 1e-6 * max(1.0, abs(float(want[2]))) + 1e-3, (got, want)
+    assert st.gather().shape == (1, 4)

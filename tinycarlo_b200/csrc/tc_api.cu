@@ -443,7 +443,9 @@ int tc_create(const TcMapDesc *map, const TcSimDesc *sim, int32_t num_envs, int3
     TC_CUDAH(tc_allow_max_smem(tc_track_thread_kernel));
     TC_CUDAH(cudaFuncSetAttribute(tc_track_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // a warp per env pays off only when there are too few envs to fill the SMs with one thread each (TC_TRACK_MODE=warp|thread overrides)
-    h->track_per_thread = num_envs >= 8192 ? 1 : 0;   // measured: 4096 envs 0.045 (warp) vs 0.062 ms (thread), 32768 envs 0.187 vs 0.044 ms
+    // measured: 4096 envs 0.033 (8 lanes per env) vs 0.062 ms (thread), 8192 envs 0.035 vs 0.062, 32768 envs 0.187 (warp) vs 0.044 ms:
+    // a thread per env once 8 lanes per env would need more than one wave of warps (3 blocks x 8 warps per SM)
+    h->track_per_thread = num_envs / 4 > 3 * 8 * h->n_sms ? 1 : 0;
     if (const char *tm = getenv("TC_TRACK_MODE")) h->track_per_thread = (tm[0] == 't' || tm[0] == '1') ? 1 : 0;
     // below that: 8 lanes per env once a warp per env would need more than one wave of warps (3 blocks x 8 warps per SM), else a warp per env
     h->track_group = num_envs > 3 * 8 * h->n_sms / 2 ? 8 : 32;
@@ -859,6 +861,15 @@ int tc_noise_blobs(TcHandle *h, uint8_t *dev_obs, uint64_t seed, uint32_t step, 
     na.mask = dev_mask; na.obs = dev_obs;
     tc_noise_blobs_kernel<<<h->n_envs, 256, 0, (cudaStream_t)stream>>>(na);
     h->launches++;
+    TC_CUDA(cudaGetLastError());
+    return TC_OK;
+}
+
+int tc_episode_stats(const float *dev_reward, const uint8_t *dev_terminated, const uint8_t *dev_truncated, int32_t n, double *dev_acc4, void *stream) {
+    if (!dev_reward || !dev_terminated || !dev_truncated || !dev_acc4 || n < 0) return tc_fail(TC_ERR_INVALID, "tc_episode_stats: bad argument");
+    if (n == 0) return TC_OK;
+    const int blocks = std::min((n + 255) / 256, 64);   // the sum of rewards is a float64 atomic per block: order-dependent in the last bits only
+    tc_episode_stats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dev_reward, dev_terminated, dev_truncated, n, dev_acc4);
     TC_CUDA(cudaGetLastError());
     return TC_OK;
 }

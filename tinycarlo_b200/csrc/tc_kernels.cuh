@@ -1864,6 +1864,35 @@ __global__ void __launch_bounds__(256) tc_noise_blobs_kernel(const TcNoiseArgs a
         }
 }
 
+// ------------------------------------------------------------------------------------------------ episode statistics
+// The per-rank episode statistics that the ranks all-gather at log cadence (episodes finished, truncations, reward sum, env-steps)
+// from a step's reward / terminated / truncated tensors in ONE launch: as torch ops this bookkeeping is eight tiny kernels per
+// step, a fifth of the device time of a 4096-env step of small frames.
+__global__ void __launch_bounds__(256) tc_episode_stats_kernel(const float *reward, const uint8_t *terminated, const uint8_t *truncated, int n, double *acc4) {
+    double ep = 0, tr = 0, rw = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const bool t = truncated[i] != 0;
+        ep += (terminated[i] != 0 || t) ? 1.0 : 0.0;
+        tr += t ? 1.0 : 0.0;
+        rw += (double)reward[i];
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        ep += __shfl_xor_sync(0xffffffffu, ep, off);
+        tr += __shfl_xor_sync(0xffffffffu, tr, off);
+        rw += __shfl_xor_sync(0xffffffffu, rw, off);
+    }
+    __shared__ double s[3][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s[0][warp] = ep; s[1][warp] = tr; s[2][warp] = rw; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0;
+        for (int w = 0; w < 8; w++) v += s[threadIdx.x][w];
+        atomicAdd(acc4 + threadIdx.x, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 3) atomicAdd(acc4 + 3, (double)n);
+}
+
 // ------------------------------------------------------------------------------------------------ test hook
 // layer.py known-answer queries on class 0 (tests only)
 __global__ void tc_debug_layer_kernel(const unsigned char *blob, TcBlobLayout L, int op, double px, double py, double ang, int i0, int i1,
