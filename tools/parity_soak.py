@@ -71,6 +71,8 @@ st["seconds"] = round(time.time() - t0, 1)
 st["info_error_per_field"] = per_field
 st["max_rel_info_note"] = "max over all info fields of |gpu - oracle| / max(|oracle|, 1e-6): dominated by values near zero (see info_error_per_field: max_abs, and max_rel over |value| > 1e-3)"
 st["kernels"] = env.render_info()
+from tinycarlo_b200 import _lib
+st["library_so_hash"] = _lib.build_info()
 st["obs_format"] = FMT
 st["config"] = f"{mp} {H}x{W} classes, {n} envs x {steps} steps, Stanley + noise, maneuver changes every 25 steps, 5% reverse bursts"
 print(json.dumps(st))
