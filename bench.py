@@ -287,6 +287,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5], help="BASELINE.json config (1-based); 3 is the one the metric is quoted on")
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="override the config's env count per GPU")
+    ap.add_argument("--graph-steps", type=int, default=5, help="env steps captured per CUDA-graph replay (launch-bound configs)")
     ap.add_argument("--min-seconds", type=float, default=3.0, help="length of the sustained device-timed run reported next to the K-step one")
     ap.add_argument("--cpu-envs", type=int, default=0, help="envs of the C-port sample (default: 128 x host threads, at most 2048: 3 GB of frames)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="length of the cpu_baseline samples")
@@ -407,12 +408,13 @@ def main():
     # ---- launch-bound configs: the policy + step captured in a CUDA graph (TinyCarloVecEnv.capture), replayed
     graph = None
     if graph_stepped(w, N):
-        g = bases[0].capture(lambda e: act(), steps=1)
+        per = args.graph_steps if args.graph_steps > 0 and args.steps % args.graph_steps == 0 else 1   # env steps per replay; K stays exact
+        g = bases[0].capture(lambda e: act(), steps=per)
         for _ in range(3):
             g.replay()
         barrier()
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(args.steps // per):
             g.replay()
         e1.record()
         barrier()
@@ -420,7 +422,7 @@ def main():
         if world > 1:
             dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
         graph = {"value": N * world * args.steps / (float(g_ms.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(g_ms.item()) / args.steps,
-                 "note": "policy ops + step captured once with TinyCarloVecEnv.capture() and replayed: one launch per step"}
+                 "note": f"policy ops + step captured once with TinyCarloVecEnv.capture(steps={per}) and replayed: one graph launch per {per} step(s)"}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- config 5: per-group kernel times from a serial pass (the groups normally overlap on separate streams)
