@@ -238,3 +238,27 @@ def test_gymnasium_registration_with_a_gymnasium_on_the_path():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "tests", "golden", "gym_stub"), root]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_bench_product_arm_is_free_of_test_infrastructure():
+    """the product arm of bench.py must not build its workload from tests/ or load the oracle. bench.py imports neither at
+    module level, never puts tests/ on the path, and only its CPU arm (port_arm) names the oracle package."""
+    import ast
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "bench.py")).read()
+    assert "pair_util" not in src and '"tests"' not in src
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name != "port_arm":
+            for sub in ast.walk(node):
+                if isinstance(sub, (ast.Import, ast.ImportFrom)):
+                    names = [a.name for a in sub.names] + [getattr(sub, "module", "") or ""]
+                    assert not any(n.split(".")[0] == "oracle" for n in names), (node.name, names)
+    out = subprocess.run([sys.executable, "-c", "import sys, bench; print(sorted(m for m in sys.modules if m.split('.')[0] in ('oracle', 'pair_util', 'golden_util')))"],
+                         cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "[]", (out.stdout, out.stderr[-500:])
+    for f in os.listdir(os.path.join(root, "tools")):     # the tools parse
+        if f.endswith(".py"):
+            ast.parse(open(os.path.join(root, "tools", f)).read())
